@@ -1,0 +1,201 @@
+/*
+ * pointslam_b200.h -- C ABI of libpointslam_b200.so
+ *
+ * The B200-native (sm_100a) implementation of Point-SLAM's per-frame volumetric
+ * rendering hot path.  The reference has NO native interface for this path: it is
+ * a Python duck-typed API (src/neural_point.py, src/conv_onet/models/decoder.py,
+ * src/utils/Renderer.py) whose GPU work is done by faiss-gpu 1.7.2 and ATen.  Each
+ * entry point below names the reference call site it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all arithmetic tensors are contiguous float32, indices int32, radii float64
+ *     (the reference's dynamic radii are float64 tensors, Tracker.py:247-250);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), except
+ *     psl_grid_sort which returns a host count and therefore synchronises;
+ *   - the library allocates nothing the caller can see: scratch is passed in as
+ *     (ws, ws_bytes), sized by the matching *_ws_bytes query;
+ *   - return value 0 = success, negative = error (psl_last_error() gives the text);
+ *   - no global mutable state except the per-thread last-error string: one process
+ *     per GPU, any number of processes per box.
+ */
+#ifndef POINTSLAM_B200_H
+#define POINTSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSL_NN 8          /* pointcloud.nn_num   (configs/point_slam.yaml:107) */
+#define PSL_CDIM 32       /* model.c_dim         (configs/point_slam.yaml:10)  */
+#define PSL_GEO_EMB 93    /* decoder.py:101 */
+#define PSL_COL_EMB 20    /* decoder.py:303 */
+#define PSL_REL_EMB 10    /* decoder.py:313-314 */
+#define PSL_GEO_HID 32    /* decoder.py:469 */
+#define PSL_COL_HID 128   /* decoder.py:472 */
+
+typedef void* psl_stream_t;
+
+int psl_version(void);
+const char* psl_last_error(void);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int psl_device_sm_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * K0  spatial hash of the neural point cloud
+ * replaces: faiss GpuIndexIVFFlat train/add, src/neural_point.py:37-41,161-164
+ * ------------------------------------------------------------------------- */
+typedef struct psl_grid {
+    const float* sorted_pts;      /* (n,4) float4: x,y,z,bitcast(original index); sorted by cell key */
+    const uint64_t* table_keys;   /* (capacity) cell key or ~0 for empty                              */
+    const uint32_t* table_vals;   /* (capacity,2) start,count into sorted_pts                         */
+    uint32_t capacity;            /* power of two                                                     */
+    int32_t n;                    /* number of points                                                 */
+    float cell;                   /* cell edge length in metres                                       */
+} psl_grid;
+
+size_t psl_grid_sort_ws_bytes(int64_t n);
+/* step 1: keys, radix sort, gather.  Writes sorted_pts (n,4), sorted_keys (n) and returns the number
+ * of occupied cells through *n_cells_host (synchronises `stream`). */
+int psl_grid_sort(const float* cloud_pos, int64_t n, float cell, float* sorted_pts, uint64_t* sorted_keys,
+                  void* ws, size_t ws_bytes, int64_t* n_cells_host, psl_stream_t stream);
+/* step 2: fill the open-addressing table (capacity = power of two >= 2*n_cells, caller-allocated). */
+int psl_grid_hash(const uint64_t* sorted_keys, int64_t n, uint64_t* table_keys, uint32_t* table_vals,
+                  uint32_t capacity, psl_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K1  ray-march + exact radius-kNN
+ * replaces: Renderer.render_batch_ray sample placement (src/utils/Renderer.py:133-174) and
+ *           NeuralPointCloud.find_neighbors_faiss (src/neural_point.py:169-215)
+ *
+ * Radius: r2 == NULL -> every query uses r2_scalar; else query m uses r2[m / r2_group].
+ * Outputs per query: I (8) ascending by (D, index), -1 padded; D (8) squared L2 with the canonical
+ * fp32 formula ((dx*dx+dy*dy)+dz*dz), FLT_MAX padded; nnum = #(D < r2) (strict, float64 compare).
+ * Only neighbours with D <= r2 are reported (slots beyond the radius carry zero weight downstream).
+ * ------------------------------------------------------------------------- */
+int psl_knn_query(const psl_grid* grid_host, const float* pos, int64_t m, const double* r2, double r2_scalar,
+                  int32_t r2_group, int32_t* I, float* D, int32_t* nnum, psl_stream_t stream);
+
+/* rays: z = near*d*(1-t) + far*d*t for gt_depth>0 (operator order of Renderer.py:140-142), else the
+ * row z_override[r] (may be NULL when all depths are > 0).  Writes z_vals (R,S), pos (R*S,3), I, D, nnum. */
+int psl_raymarch_knn(const psl_grid* grid_host, const float* rays_o, const float* rays_d, const float* gt_depth,
+                     int64_t n_rays, int32_t n_samples, const float* t_vals, float near_surface, float far_surface,
+                     const float* z_override, const double* r2_ray, double r2_scalar,
+                     float* z_vals, float* pos, int32_t* I, float* D, int32_t* nnum, psl_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2+K3  IDW interpolation + per-neighbour colour MLP + geometry/colour MLP decode
+ * replaces: POINT.forward (src/conv_onet/models/decoder.py:476-518) incl. get_feature_at_pos (:130-173,
+ *           :341-390), GaussianFourierFeatureTransform (:30-37), MLP_geometry.forward (:175-222),
+ *           MLP_color.forward (:392-449) and their autograd backward.
+ * ------------------------------------------------------------------------- */
+typedef struct psl_decoder_params {        /* row-major (out,in) exactly like the reference state_dict */
+    const float* g_B;                      /* geo_decoder.embedder._B            (3,93)   */
+    const float* g_W[5];                   /* geo_decoder.pts_linears.i.weight   (32,93|32|32|125|32) */
+    const float* g_b[5];
+    const float* g_Wc[5];                  /* geo_decoder.fc_c.i.weight          (32,32)  */
+    const float* g_bc[5];
+    const float* g_Wo;                     /* geo_decoder.output_linear.weight   (1,32)   */
+    const float* g_bo;
+    const float* c_B;                      /* color_decoder.embedder._B          (3,20)   */
+    const float* c_Brel;                   /* color_decoder.embedder_rel_pos._B  (3,10)   */
+    const float* c_N1;                     /* mlp_col_neighbor.linear1.weight    (128,52) */
+    const float* c_n1b;
+    const float* c_N2;                     /* mlp_col_neighbor.linear2.weight    (32,128) */
+    const float* c_n2b;
+    const float* c_W[5];                   /* color_decoder.pts_linears.i.weight (128,40|128|128|168|128) */
+    const float* c_b[5];
+    const float* c_Wc[5];                  /* color_decoder.fc_c.i.weight        (128,32) */
+    const float* c_bc[5];
+    const float* c_Wo;                     /* color_decoder.output_linear.weight (3,128)  */
+    const float* c_bo;
+} psl_decoder_params;
+
+/* same field order, float* destinations; a NULL entry means "gradient not wanted" */
+typedef struct psl_decoder_grads {
+    float* g_B; float* g_W[5]; float* g_b[5]; float* g_Wc[5]; float* g_bc[5]; float* g_Wo; float* g_bo;
+    float* c_B; float* c_Brel; float* c_N1; float* c_n1b; float* c_N2; float* c_n2b;
+    float* c_W[5]; float* c_b[5]; float* c_Wc[5]; float* c_bc[5]; float* c_Wo; float* c_bo;
+} psl_decoder_grads;
+
+enum { PSL_STAGE_GEOMETRY = 0, PSL_STAGE_COLOR = 1 };
+enum { PSL_RGB_SIGMOID = 0,      /* decoder.py:447                                     */
+       PSL_RGB_AFFINE_SIGMOID = 1,/* sigmoid(out @ rot + trans), decoder.py:433-438     */
+       PSL_RGB_RAW = 2 };        /* encode_exposure with exposure_feat None, :439-445  */
+enum { PSL_WEIGHT_DISTANCE = 0, PSL_WEIGHT_EXPO = 1 };   /* pointcloud.nn_weighting, decoder.py:152-156 */
+
+typedef struct psl_decode_cfg {
+    int32_t stage;            /* PSL_STAGE_*                                                         */
+    int32_t encode_rel_pos;   /* model.encode_rel_pos_in_col                                         */
+    int32_t rgb_mode;         /* PSL_RGB_*                                                           */
+    int32_t weighting;        /* PSL_WEIGHT_*                                                        */
+    int32_t min_nn;           /* pointcloud.min_nn_num (2)                                           */
+    int32_t r2_group;         /* r2[m / r2_group]; ignored when r2 == NULL                            */
+    int32_t is_tracker;       /* backward only: propagate to pos through the recomputed D (:143-148) */
+    int32_t reserved;
+    double r2_scalar;
+} psl_decode_cfg;
+
+size_t psl_packed_params_floats(void);
+/* floats of activations kept per sample for the backward (0 when save == NULL is passed to forward) */
+size_t psl_decode_save_floats_per_sample(const psl_decode_cfg* cfg);
+size_t psl_decode_bwd_ws_bytes(int64_t m);
+
+/* repack the reference-layout parameters into the transposed/padded blob the kernels stage in shared memory */
+int psl_pack_params(const psl_decoder_params* params_host, float* packed, psl_stream_t stream);
+
+/* forward.  raw (m,4) = [rgb, occ]; has_nb (m) uint8.  exposure_affine: 12 floats (rot row-major 3x3, trans 3)
+ * or NULL.  rand_geo / rand_col: the N(0,0.01^2) vectors given to samples without neighbours (decoder.py:170,387).
+ * save: NULL (inference) or m * psl_decode_save_floats_per_sample floats. */
+int psl_decode_fwd(const psl_decode_cfg* cfg, const float* packed, const float* pos, int64_t m,
+                   const int32_t* I, const float* D, const int32_t* nnum, const double* r2,
+                   const float* cloud_pos, const float* geo_feats, const float* col_feats,
+                   const float* rand_geo, const float* rand_col, const float* exposure_affine,
+                   float* raw, uint8_t* has_nb, float* save, psl_stream_t stream);
+
+/* backward.  d_raw (m,4).  Outputs (any may be NULL): d_pos (m,3); pair gradients for the deterministic
+ * feature scatter: d_cg (m,32) (geometry feature grad before IDW), wn (m,8) normalised weights,
+ * d_colpair (m,8,32) (gradient w.r.t. col_feats[I[m,k]]); parameter grads via psl_decoder_grads;
+ * d_exposure_affine (12).  ws: psl_decode_bwd_ws_bytes(m). */
+int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_params* params_host, const float* packed,
+                   const float* pos, int64_t m, const int32_t* I, const float* D, const int32_t* nnum,
+                   const double* r2, const float* cloud_pos, const float* geo_feats, const float* col_feats,
+                   const float* exposure_affine, const float* raw, const float* save, const float* d_raw,
+                   float* d_pos, float* d_cg, float* wn, float* d_colpair,
+                   const psl_decoder_grads* grads_host, float* d_exposure_affine,
+                   void* ws, size_t ws_bytes, psl_stream_t stream);
+
+/* deterministic scatter of per-(sample,neighbour) feature gradients into dense (n_points,32) tensors
+ * (replaces ATen's sort-based index_put_(accumulate=True) backward of feats[I], decoder.py:164,372).
+ * d_geo / d_col must be zero-filled by the caller; either may be NULL. */
+size_t psl_feat_scatter_ws_bytes(int64_t m);
+int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, const float* wn, const float* d_cg,
+                     const float* d_colpair, const float* d_cc, float* d_geo, float* d_col,
+                     void* ws, size_t ws_bytes, psl_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * alpha composite      replaces: raw2outputs_nerf_color (src/common.py:298-336) + the -100 masking of
+ *                      Renderer.py:189-190 (mask applied to the VALUE only, gradient passes through)
+ * ------------------------------------------------------------------------- */
+int psl_composite_fwd(const float* raw, const uint8_t* has_nb, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                      float coef, float* depth, float* var, float* rgb, float* weights, psl_stream_t stream);
+int psl_composite_bwd(const float* raw, const uint8_t* has_nb, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                      float coef, const float* d_depth, const float* d_var, const float* d_rgb,
+                      float* d_raw, psl_stream_t stream);
+
+/* d_rays_o = sum_s d_pos, d_rays_d = sum_s z * d_pos   (backward of Renderer.py:172-174) */
+int psl_rays_bwd(const float* d_pos, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                 float* d_rays_o, float* d_rays_d, psl_stream_t stream);
+
+/* ray validity: >= int(S/2+1) samples with neighbours (decoder.py:200-201) */
+int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_samples, int32_t min_count, uint8_t* ray_mask,
+                 psl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTSLAM_B200_H */

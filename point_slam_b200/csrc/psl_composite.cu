@@ -1,0 +1,238 @@
+// Alpha composite (src/common.py:298-336) with the "-100 where no neighbours" masking of
+// src/utils/Renderer.py:189-190, its backward, the ray backward of p = o + d z, the ray validity mask
+// (decoder.py:200-201) and the deterministic feature-gradient scatter.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "psl_common.cuh"
+
+namespace psl {
+
+constexpr int MAX_S = 64;
+
+__global__ void k_composite_fwd(const float4* __restrict__ raw, const unsigned char* __restrict__ has_nb,
+                                const float* __restrict__ z_vals, long long R, int S, float coef,
+                                float* __restrict__ depth, float* __restrict__ var, float* __restrict__ rgb,
+                                float* __restrict__ weights) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float T = 1.f, wsum = 0.f, A = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float4 v = raw[r * S + s];
+        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
+        const float al = sigmoidf_(__fmul_rn(coef, occ));
+        const float w = __fmul_rn(al, T);
+        T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
+        const float z = z_vals[r * S + s];
+        wsum = __fadd_rn(wsum, w);
+        A = __fadd_rn(A, __fmul_rn(w, z));
+        cr = __fadd_rn(cr, __fmul_rn(w, v.x));
+        cg = __fadd_rn(cg, __fmul_rn(w, v.y));
+        cb = __fadd_rn(cb, __fmul_rn(w, v.z));
+        if (weights) weights[r * S + s] = w;
+    }
+    wsum = __fadd_rn(wsum, 1e-10f);
+    const float d = __fdiv_rn(A, wsum);
+    float vv = 0.f, T2 = 1.f;
+    for (int s = 0; s < S; ++s) {
+        const float4 v = raw[r * S + s];
+        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
+        const float al = sigmoidf_(__fmul_rn(coef, occ));
+        const float w = __fmul_rn(al, T2);
+        T2 = __fmul_rn(T2, __fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
+        const float t = __fsub_rn(z_vals[r * S + s], d);
+        vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(w, t), t));
+    }
+    depth[r] = d;
+    var[r] = vv;
+    rgb[r * 3] = __fdiv_rn(cr, wsum);
+    rgb[r * 3 + 1] = __fdiv_rn(cg, wsum);
+    rgb[r * 3 + 2] = __fdiv_rn(cb, wsum);
+}
+
+__global__ void k_composite_bwd(const float4* __restrict__ raw, const unsigned char* __restrict__ has_nb,
+                                const float* __restrict__ z_vals, long long R, int S, float coef,
+                                const float* __restrict__ d_depth, const float* __restrict__ d_var,
+                                const float* __restrict__ d_rgb, float4* __restrict__ d_raw) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float al[MAX_S], Tr[MAX_S];
+    float T = 1.f, wsum = 0.f, A = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float4 v = raw[r * S + s];
+        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
+        const float a_ = sigmoidf_(coef * occ);
+        al[s] = a_; Tr[s] = T;
+        const float w = a_ * T;
+        T *= (1.0f - a_) + 1e-10f;
+        wsum += w; A += w * z_vals[r * S + s];
+        cr += w * v.x; cg += w * v.y; cb += w * v.z;
+    }
+    wsum += 1e-10f;
+    const float inv = 1.0f / wsum;
+    const float dep = A * inv, Rr = cr * inv, Rg = cg * inv, Rb = cb * inv;
+    const float gv = d_var ? d_var[r] : 0.f;
+    float sw = 0.f;                                   // sum_s w_s (z_s - depth)
+    for (int s = 0; s < S; ++s) sw += al[s] * Tr[s] * (z_vals[r * S + s] - dep);
+    const float gd = (d_depth ? d_depth[r] : 0.f) - 2.0f * gv * sw;
+    const float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
+    const float dA = gd * inv, dBr = gr * inv, dBg = gg * inv, dBb = gb * inv;
+    const float dWs = -(gd * dep + gr * Rr + gg * Rg + gb * Rb) * inv;
+    float G = 0.f;                                    // sum_{s>j} dT_s * T_s
+    for (int s = S - 1; s >= 0; --s) {
+        const float4 v = raw[r * S + s];
+        const float z = z_vals[r * S + s];
+        const float w = al[s] * Tr[s];
+        const float t = z - dep;
+        const float dw = gv * t * t + dA * z + dBr * v.x + dBg * v.y + dBb * v.z + dWs;
+        const float u = (1.0f - al[s]) + 1e-10f;
+        const float da = dw * Tr[s] - G / u;
+        G += dw * al[s] * Tr[s];
+        const float docc = da * al[s] * (1.0f - al[s]) * coef;
+        d_raw[r * S + s] = make_float4(w * dBr, w * dBg, w * dBb, docc);
+    }
+}
+
+__global__ void k_rays_bwd(const float* __restrict__ d_pos, const float* __restrict__ z_vals, long long R, int S,
+                           float* __restrict__ d_o, float* __restrict__ d_d) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float z = z_vals[r * S + s];
+        const float gx = d_pos[(r * S + s) * 3], gy = d_pos[(r * S + s) * 3 + 1], gz = d_pos[(r * S + s) * 3 + 2];
+        ox += gx; oy += gy; oz += gz;
+        dx += z * gx; dy += z * gy; dz += z * gz;
+    }
+    if (d_o) { d_o[r * 3] = ox; d_o[r * 3 + 1] = oy; d_o[r * 3 + 2] = oz; }
+    if (d_d) { d_d[r * 3] = dx; d_d[r * 3 + 1] = dy; d_d[r * 3 + 2] = dz; }
+}
+
+__global__ void k_ray_mask(const unsigned char* __restrict__ has_nb, long long R, int S, int min_count,
+                           unsigned char* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int c = 0;
+    for (int s = 0; s < S; ++s) c += has_nb[r * S + s] ? 1 : 0;
+    out[r] = c >= min_count;
+}
+
+// ---- deterministic feature-gradient scatter ----------------------------------------------------------------
+__global__ void k_pair_keys(const int* __restrict__ I, const float* __restrict__ wn, long long n_pairs, unsigned n_points,
+                            unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int idx = I[p];
+    keys[p] = (idx >= 0 && wn[p] != 0.f) ? (unsigned)idx : n_points;
+    vals[p] = (unsigned)p;
+}
+
+__global__ void k_scatter_segments(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
+                                   long long n_pairs, unsigned n_points, const float* __restrict__ wn,
+                                   const float* __restrict__ d_cg, const float* __restrict__ d_colpair,
+                                   const float* __restrict__ d_cc, float* __restrict__ d_geo, float* __restrict__ d_col) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_pairs; p += nwarps) {
+        const unsigned key = keys[p];
+        if (key >= n_points) continue;
+        if (p > 0 && keys[p - 1] == key) continue;
+        float ag = 0.f, ac = 0.f;
+        for (long long j = p; j < n_pairs && keys[j] == key; ++j) {
+            const unsigned pid = vals[j];
+            const float w = wn[pid];
+            const long long m = pid >> 3;
+            if (d_geo) ag += w * d_cg[m * 32 + lane];
+            if (d_col) ac += d_colpair ? d_colpair[(long long)pid * 32 + lane] : w * d_cc[m * 32 + lane];
+        }
+        if (d_geo) d_geo[(long long)key * 32 + lane] = ag;
+        if (d_col) d_col[(long long)key * 32 + lane] = ac;
+    }
+}
+
+}  // namespace psl
+
+using namespace psl;
+
+static inline unsigned nblk(long long n, int tb) { return (unsigned)((n + tb - 1) / tb); }
+
+extern "C" int psl_composite_fwd(const float* raw, const uint8_t* has_nb, const float* z_vals, int64_t n_rays,
+                                 int32_t n_samples, float coef, float* depth, float* var, float* rgb, float* weights,
+                                 psl_stream_t stream) {
+    PSL_REQUIRE(raw && has_nb && z_vals && depth && var && rgb, "NULL argument");
+    if (n_rays == 0) return 0;
+    k_composite_fwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(raw), has_nb, z_vals,
+                                                                     n_rays, n_samples, coef, depth, var, rgb, weights);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int psl_composite_bwd(const float* raw, const uint8_t* has_nb, const float* z_vals, int64_t n_rays,
+                                 int32_t n_samples, float coef, const float* d_depth, const float* d_var,
+                                 const float* d_rgb, float* d_raw, psl_stream_t stream) {
+    PSL_REQUIRE(raw && has_nb && z_vals && d_raw, "NULL argument");
+    PSL_REQUIRE(n_samples <= MAX_S, "n_samples > 64 not supported by the composite backward");
+    if (n_rays == 0) return 0;
+    k_composite_bwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(raw), has_nb, z_vals,
+                                                                     n_rays, n_samples, coef, d_depth, d_var, d_rgb,
+                                                                     reinterpret_cast<float4*>(d_raw));
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int psl_rays_bwd(const float* d_pos, const float* z_vals, int64_t n_rays, int32_t n_samples, float* d_rays_o,
+                            float* d_rays_d, psl_stream_t stream) {
+    PSL_REQUIRE(d_pos && z_vals, "NULL argument");
+    if (n_rays == 0) return 0;
+    k_rays_bwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(d_pos, z_vals, n_rays, n_samples, d_rays_o, d_rays_d);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_samples, int32_t min_count,
+                            uint8_t* ray_mask, psl_stream_t stream) {
+    PSL_REQUIRE(has_nb && ray_mask, "NULL argument");
+    if (n_rays == 0) return 0;
+    k_ray_mask<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(has_nb, n_rays, n_samples, min_count, ray_mask);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t psl_feat_scatter_ws_bytes(int64_t m) {
+    const long long np = m * 8;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                    (const unsigned*)nullptr, (unsigned*)nullptr, (int)np, 0, 32);
+    return 4 * al256(sizeof(unsigned) * np) + al256(cub_bytes) + 256;
+}
+
+extern "C" int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, const float* wn, const float* d_cg,
+                                const float* d_colpair, const float* d_cc, float* d_geo, float* d_col, void* ws,
+                                size_t ws_bytes, psl_stream_t stream) {
+    PSL_REQUIRE(I && wn && ws, "NULL argument");
+    PSL_REQUIRE(!d_geo || d_cg, "d_geo needs d_cg");
+    PSL_REQUIRE(!d_col || d_colpair || d_cc, "d_col needs d_colpair or d_cc");
+    PSL_REQUIRE(m * 8 < (1ll << 31) && n_points < (1ll << 31), "too many pairs/points");
+    if (m == 0 || (!d_geo && !d_col)) return 0;
+    PSL_REQUIRE(ws_bytes >= psl_feat_scatter_ws_bytes(m), "workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const long long np = m * 8;
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    unsigned* k_in = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
+    unsigned* k_out = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
+    unsigned* v_in = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
+    unsigned* v_out = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
+    size_t cub_bytes = ws_bytes - (size_t)(w - static_cast<unsigned char*>(ws));
+    k_pair_keys<<<nblk(np, 256), 256, 0, st>>>(I, wn, np, (unsigned)n_points, k_in, v_in);
+    int bits = 1;
+    while ((1ll << bits) <= n_points) ++bits;
+    PSL_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, k_in, k_out, v_in, v_out, (int)np, 0, bits, st));
+    long long blocks = (np * 32 + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_scatter_segments<<<(unsigned)blocks, 256, 0, st>>>(k_out, v_out, np, (unsigned)n_points, wn, d_cg, d_colpair, d_cc,
+                                                        d_geo, d_col);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,420 @@
+"""Host-side wrappers over the C ABI: spatial hash, kNN, fused render (autograd), decode (autograd), composite.
+
+PyTorch is used for device memory, streams and the autograd graph only; every arithmetic step of the hot path runs
+in libpointslam_b200.so.  There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+PARAM_ORDER = (['g_B'] + [f'g_W{i}' for i in range(5)] + [f'g_b{i}' for i in range(5)] +
+               [f'g_Wc{i}' for i in range(5)] + [f'g_bc{i}' for i in range(5)] + ['g_Wo', 'g_bo', 'c_B', 'c_Brel',
+               'c_N1', 'c_n1b', 'c_N2', 'c_n2b'] + [f'c_W{i}' for i in range(5)] + [f'c_b{i}' for i in range(5)] +
+               [f'c_Wc{i}' for i in range(5)] + [f'c_bc{i}' for i in range(5)] + ['c_Wo', 'c_bo'])
+assert len(PARAM_ORDER) == L.N_PARAMS
+
+
+def decoder_param_list(decoders) -> List[torch.Tensor]:
+    """The 51 tensors of a POINT module in psl_decoder_params order (reference names in the comments of
+    include/pointslam_b200.h)."""
+    g, c = decoders.geo_decoder, decoders.color_decoder
+    out = [g.embedder._B]
+    out += [g.pts_linears[i].weight for i in range(5)] + [g.pts_linears[i].bias for i in range(5)]
+    out += [g.fc_c[i].weight for i in range(5)] + [g.fc_c[i].bias for i in range(5)]
+    out += [g.output_linear.weight, g.output_linear.bias]
+    out += [c.embedder._B, c.embedder_rel_pos._B, c.mlp_col_neighbor.linear1.weight, c.mlp_col_neighbor.linear1.bias,
+            c.mlp_col_neighbor.linear2.weight, c.mlp_col_neighbor.linear2.bias]
+    out += [c.pts_linears[i].weight for i in range(5)] + [c.pts_linears[i].bias for i in range(5)]
+    out += [c.fc_c[i].weight for i in range(5)] + [c.fc_c[i].bias for i in range(5)]
+    out += [c.output_linear.weight, c.output_linear.bias]
+    return out
+
+
+def state_dict_param_list(P: dict, device) -> List[torch.Tensor]:
+    """Same list from a flat dict keyed like the reference state_dict (+ 'color_decoder.embedder._B')."""
+    g, c = 'geo_decoder.', 'color_decoder.'
+    keys = [g + 'embedder._B'] + [g + f'pts_linears.{i}.weight' for i in range(5)] + \
+        [g + f'pts_linears.{i}.bias' for i in range(5)] + [g + f'fc_c.{i}.weight' for i in range(5)] + \
+        [g + f'fc_c.{i}.bias' for i in range(5)] + [g + 'output_linear.weight', g + 'output_linear.bias'] + \
+        [c + 'embedder._B', c + 'embedder_rel_pos._B', c + 'mlp_col_neighbor.linear1.weight',
+         c + 'mlp_col_neighbor.linear1.bias', c + 'mlp_col_neighbor.linear2.weight', c + 'mlp_col_neighbor.linear2.bias'] + \
+        [c + f'pts_linears.{i}.weight' for i in range(5)] + [c + f'pts_linears.{i}.bias' for i in range(5)] + \
+        [c + f'fc_c.{i}.weight' for i in range(5)] + [c + f'fc_c.{i}.bias' for i in range(5)] + \
+        [c + 'output_linear.weight', c + 'output_linear.bias']
+    return [P[k].to(device=device, dtype=torch.float32).contiguous() for k in keys]
+
+
+def _param_struct(tensors: Sequence[Optional[torch.Tensor]]) -> L.DecoderParams:
+    s = L.DecoderParams()
+    flat = [None if t is None else t.data_ptr() for t in tensors]
+    it = iter(flat)
+    for name, ctype in L.DecoderParams._fields_:
+        if ctype is L._vp:
+            setattr(s, name, next(it))
+        else:
+            arr = getattr(s, name)
+            for i in range(5):
+                arr[i] = next(it)
+    return s
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# spatial hash
+# ------------------------------------------------------------------------------------------------------------------
+class SpatialHash:
+    """GPU-resident hash grid over the neural point cloud (K0).  Rebuilt on every append (about 1 ms for 2 M points);
+    point indices are stable (the grid stores a sorted copy carrying the original index)."""
+
+    def __init__(self, cell: float = 0.08):
+        self.cell = float(cell)
+        self.n = 0
+        self.sorted_pts = self.table_keys = self.table_vals = None
+        self.capacity = 0
+        self.struct = L.Grid(None, None, None, 0, 0, self.cell)
+
+    def build(self, cloud_pos: torch.Tensor):
+        lib = L.load()
+        pos = _f32c(cloud_pos).reshape(-1, 3)
+        n = pos.shape[0]
+        dev = pos.device
+        self.n = n
+        if n == 0:
+            self.struct = L.Grid(None, None, None, 0, 0, self.cell)
+            return self
+        ws_bytes = lib.psl_grid_sort_ws_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.sorted_pts = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        n_cells = C.c_int64(0)
+        L.check(lib.psl_grid_sort(L.ptr(pos), n, self.cell, L.ptr(self.sorted_pts), L.ptr(keys), L.ptr(ws), ws_bytes,
+                                  C.byref(n_cells), L.stream()), 'psl_grid_sort')
+        cap = 1 << max(4, int(math.ceil(math.log2(max(2 * n_cells.value, 2)))))
+        self.capacity = cap
+        self.table_keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.table_vals = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        L.check(lib.psl_grid_hash(L.ptr(keys), n, L.ptr(self.table_keys), L.ptr(self.table_vals), cap, L.stream()),
+                'psl_grid_hash')
+        self.n_cells = n_cells.value
+        self.struct = L.Grid(self.sorted_pts.data_ptr(), self.table_keys.data_ptr(), self.table_vals.data_ptr(),
+                             cap, n, self.cell)
+        return self
+
+
+def _r2_args(radius, dynamic_radius, M_groups, device):
+    """(r2 tensor or None, r2_scalar) with the comparison semantics of neural_point.py:208-213."""
+    if dynamic_radius is not None:
+        r2 = (dynamic_radius.detach().reshape(-1).to(device=device, dtype=torch.float64) ** 2).contiguous()
+        assert r2.shape[0] == M_groups, 'shape mis-match for input points and dynamic radius'
+        return r2, 0.0
+    return None, float(np.float32(radius ** 2))
+
+
+def knn_query(grid: SpatialHash, pos: torch.Tensor, radius: float = 0.08, dynamic_radius=None, group: int = 1):
+    """find_neighbors_faiss kernel (a5): -> D (M,8) f32, I (M,8) i32, neighbor_num (M,) i32.
+    `group`: consecutive queries that belong together (samples of one ray); dynamic_radius then has M/group rows."""
+    lib = L.load()
+    pos = _f32c(pos).reshape(-1, 3)
+    M = pos.shape[0]
+    dev = pos.device
+    I = torch.empty((M, 8), dtype=torch.int32, device=dev)
+    D = torch.empty((M, 8), dtype=torch.float32, device=dev)
+    nn = torch.empty((M,), dtype=torch.int32, device=dev)
+    if M == 0:
+        return D, I, nn
+    r2, r2s = _r2_args(radius, dynamic_radius, (M + group - 1) // group if dynamic_radius is not None else 0, dev)
+    L.check(lib.psl_knn_query(C.byref(grid.struct), L.ptr(pos), M, L.ptr(r2), r2s, int(group), L.ptr(I), L.ptr(D),
+                              L.ptr(nn), L.stream()), 'psl_knn_query')
+    return D, I, nn
+
+
+_T_VALS = {}
+
+
+def surface_t_vals(S: int, device) -> torch.Tensor:
+    """linspace(0,1,S) evaluated by torch on the CPU (bit-identical to the oracle), cached per device."""
+    key = (S, str(device))
+    if key not in _T_VALS:
+        _T_VALS[key] = torch.linspace(0.0, 1.0, steps=S, dtype=torch.float32).to(device)
+    return _T_VALS[key]
+
+
+_PACKED = {}
+
+
+def _packed_buffer(device):
+    key = str(device)
+    if key not in _PACKED:
+        _PACKED[key] = torch.empty(L.load().psl_packed_params_floats(), dtype=torch.float32, device=device)
+    return _PACKED[key]
+
+
+class RenderSettings:
+    """Static (non-tensor) arguments of one render call."""
+
+    def __init__(self, stage='color', S=5, near_surface=0.98, far_surface=1.02, radius_query=0.08, coef=0.1,
+                 encode_rel_pos=True, rgb_mode=L.RGB_SIGMOID, weighting='distance', min_nn=2, is_tracker=False):
+        self.stage, self.S = stage, int(S)
+        self.near_surface, self.far_surface = float(near_surface), float(far_surface)
+        self.radius_query, self.coef = float(radius_query), float(coef)
+        self.encode_rel_pos, self.rgb_mode = bool(encode_rel_pos), int(rgb_mode)
+        self.weighting, self.min_nn, self.is_tracker = weighting, int(min_nn), bool(is_tracker)
+
+    def cfg(self, r2_group, r2_scalar):
+        return L.DecodeCfg(L.STAGE[self.stage], int(self.encode_rel_pos), self.rgb_mode, L.WEIGHTING[self.weighting],
+                           self.min_nn, int(r2_group), int(self.is_tracker), 0, float(r2_scalar))
+
+
+def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
+                    affine, need_grad):
+    lib = L.load()
+    dev = pos.device
+    M = pos.shape[0]
+    packed = _packed_buffer(dev)
+    pstruct = _param_struct(params)
+    L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
+    raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
+    has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
+    save = None
+    if need_grad:
+        per = lib.psl_decode_save_floats_per_sample(C.byref(cfg))
+        save = torch.empty(max(M * per, 1), dtype=torch.float32, device=dev)
+    L.check(lib.psl_decode_fwd(C.byref(cfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                               L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(rand_geo), L.ptr(rand_col),
+                               L.ptr(affine), L.ptr(raw), L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd')
+    return raw, has_nb, save, pstruct
+
+
+def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, cloud_pos, geo, col, affine, raw, save,
+                     d_raw, want_pos, want_geo, want_col, want_affine):
+    """-> (d_pos, d_geo, d_col, param grads list, d_affine)"""
+    lib = L.load()
+    dev = pos.device
+    M = pos.shape[0]
+    color = st.stage == 'color'
+    rel = color and st.encode_rel_pos
+    d_pos = torch.empty((M, 3), dtype=torch.float32, device=dev) if want_pos else None
+    want_col = want_col and color
+    d_cg = torch.empty((M, 32), dtype=torch.float32, device=dev) if want_geo else None
+    wn = torch.empty((M, 8), dtype=torch.float32, device=dev) if (want_geo or want_col) else None
+    d_colpair = None
+    if want_col:
+        d_colpair = torch.empty((M, 8, 32) if rel else (M, 32), dtype=torch.float32, device=dev)
+    grads = [torch.zeros_like(p) if (n and (color or name.startswith('g_'))) else None
+             for p, n, name in zip(params, needs, L_PARAM_NAMES)]
+    gstruct = _param_struct(grads)
+    pstruct = _param_struct(params)
+    d_aff = torch.zeros(12, dtype=torch.float32, device=dev) if want_affine else None
+    ws_bytes = lib.psl_decode_bwd_ws_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    packed = _packed_buffer(dev)
+    L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
+                               L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
+                               L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), L.ptr(wn), L.ptr(d_colpair),
+                               C.byref(gstruct), L.ptr(d_aff), L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
+    d_geo = d_col = None
+    if want_geo or want_col:
+        d_geo = torch.zeros_like(geo) if want_geo else None
+        d_col = torch.zeros_like(col) if want_col else None
+        ws2_bytes = lib.psl_feat_scatter_ws_bytes(M)
+        ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+        L.check(lib.psl_feat_scatter(L.ptr(I), M, geo.shape[0], L.ptr(wn), L.ptr(d_cg),
+                                     L.ptr(d_colpair) if rel else None, None if rel else L.ptr(d_colpair),
+                                     L.ptr(d_geo), L.ptr(d_col), L.ptr(ws2), ws2_bytes, L.stream()), 'psl_feat_scatter')
+    return d_pos, d_geo, d_col, grads, d_aff
+
+
+L_PARAM_NAMES = PARAM_ORDER
+
+
+class _RenderFn(torch.autograd.Function):
+    """render_batch_ray core: ray-march + kNN -> decode -> composite, one autograd node."""
+
+    @staticmethod
+    def forward(ctx, st: RenderSettings, grid: SpatialHash, gt_depth, z_override, r2_ray, rand_geo, rand_col,
+                cloud_pos, rays_o, rays_d, geo_feats, col_feats, affine, *params):
+        lib = L.load()
+        dev = rays_o.device
+        R, S = rays_o.shape[0], st.S
+        M = R * S
+        ro, rd = _f32c(rays_o), _f32c(rays_d)
+        geo = _f32c(geo_feats)
+        col = _f32c(col_feats) if col_feats is not None else None
+        cloud = _f32c(cloud_pos)
+        params_c = [_f32c(p) for p in params]
+        aff = _f32c(affine).reshape(-1) if affine is not None else None
+        z_vals = torch.empty((R, S), dtype=torch.float32, device=dev)
+        pos = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        I = torch.empty((M, 8), dtype=torch.int32, device=dev)
+        D = torch.empty((M, 8), dtype=torch.float32, device=dev)
+        nn = torch.empty((M,), dtype=torch.int32, device=dev)
+        r2s = float(np.float32(st.radius_query ** 2))
+        L.check(lib.psl_raymarch_knn(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(gt_depth), R, S,
+                                     L.ptr(surface_t_vals(S, dev)), st.near_surface, st.far_surface, L.ptr(z_override),
+                                     L.ptr(r2_ray), r2s, L.ptr(z_vals), L.ptr(pos), L.ptr(I), L.ptr(D), L.ptr(nn),
+                                     L.stream()), 'psl_raymarch_knn')
+        cfg = st.cfg(S, r2s)
+        need_grad = any(ctx.needs_input_grad)
+        raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
+                                               rand_col, aff, need_grad)
+        depth = torch.empty((R,), dtype=torch.float32, device=dev)
+        var = torch.empty((R,), dtype=torch.float32, device=dev)
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(depth), L.ptr(var),
+                                      L.ptr(rgb), None, L.stream()), 'psl_composite_fwd')
+        ray_mask = torch.empty((R,), dtype=torch.uint8, device=dev)
+        L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
+        ctx.st, ctx.cfg, ctx.n_params = st, cfg, len(params)
+        ctx.save_for_backward(z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, *params_c)
+        ctx.mark_non_differentiable(ray_mask)
+        return depth, var, rgb, ray_mask.bool()
+
+    @staticmethod
+    def backward(ctx, d_depth, d_var, d_rgb, _d_mask):
+        lib = L.load()
+        st, cfg = ctx.st, ctx.cfg
+        z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save = ctx.saved_tensors[:13]
+        params = list(ctx.saved_tensors[13:])
+        R, S = z_vals.shape
+        dev = z_vals.device
+        d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
+        dd = _f32c(d_depth) if d_depth is not None else None
+        dv = _f32c(d_var) if d_var is not None else None
+        dc = _f32c(d_rgb) if d_rgb is not None else None
+        L.check(lib.psl_composite_bwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(dd), L.ptr(dv),
+                                      L.ptr(dc), L.ptr(d_raw), L.stream()), 'psl_composite_bwd')
+        nig = ctx.needs_input_grad            # (st, grid, gt_depth, z_override, r2, rand_geo, rand_col, cloud, o, d, geo, col, affine, *params)
+        want_pos = nig[8] or nig[9]
+        needs = list(nig[13:])
+        d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, cfg, params, needs, pos, I, D, nn, r2_ray, cloud, geo,
+                                                             col, aff, raw, save, d_raw, want_pos, nig[10], nig[11], nig[12])
+        d_o = d_d = None
+        if want_pos:
+            d_o = torch.empty((R, 3), dtype=torch.float32, device=dev) if nig[8] else None
+            d_d = torch.empty((R, 3), dtype=torch.float32, device=dev) if nig[9] else None
+            L.check(lib.psl_rays_bwd(L.ptr(d_pos), L.ptr(z_vals), R, S, L.ptr(d_o), L.ptr(d_d), L.stream()), 'psl_rays_bwd')
+        return (None, None, None, None, None, None, None, None, d_o, d_d, d_geo, d_col,
+                d_aff if nig[12] else None, *grads)
+
+
+class _DecodeFn(torch.autograd.Function):
+    """POINT.forward core (decoder.py:476-518) on explicit sample positions."""
+
+    @staticmethod
+    def forward(ctx, st: RenderSettings, grid: SpatialHash, r2_pts, r2_group, rand_geo, rand_col, cloud_pos,
+                p, geo_feats, col_feats, affine, *params):
+        dev = p.device
+        pos = _f32c(p).reshape(-1, 3)
+        geo = _f32c(geo_feats)
+        col = _f32c(col_feats) if col_feats is not None else None
+        cloud = _f32c(cloud_pos)
+        params_c = [_f32c(q) for q in params]
+        aff = _f32c(affine).reshape(-1) if affine is not None else None
+        D, I, nn = knn_query_r2(grid, pos, r2_pts, st.radius_query, r2_group)
+        r2s = float(np.float32(st.radius_query ** 2))
+        cfg = st.cfg(r2_group, r2s)
+        need_grad = any(ctx.needs_input_grad)
+        raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_pts, cloud, geo, col, rand_geo,
+                                               rand_col, aff, need_grad)
+        ctx.st, ctx.cfg = st, cfg
+        ctx.save_for_backward(pos, I, D, nn, r2_pts, cloud, geo, col, aff, raw, save, *params_c)
+        hb = has_nb.bool()
+        ctx.mark_non_differentiable(hb)
+        return raw, hb
+
+    @staticmethod
+    def backward(ctx, d_raw, _d_mask):
+        st, cfg = ctx.st, ctx.cfg
+        pos, I, D, nn, r2, cloud, geo, col, aff, raw, save = ctx.saved_tensors[:11]
+        params = list(ctx.saved_tensors[11:])
+        nig = ctx.needs_input_grad            # (st, grid, r2, r2_group, rand_geo, rand_col, cloud, p, geo, col, affine, *params)
+        d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, cfg, params, list(nig[11:]), pos, I, D, nn, r2, cloud,
+                                                             geo, col, aff, raw, save, _f32c(d_raw), nig[7], nig[8],
+                                                             nig[9], nig[10])
+        return (None, None, None, None, None, None, None, d_pos, d_geo, d_col, d_aff if nig[10] else None, *grads)
+
+
+def knn_query_r2(grid, pos, r2, radius, group):
+    """kNN with an already squared float64 radius tensor (or None -> scalar radius)."""
+    lib = L.load()
+    M = pos.shape[0]
+    dev = pos.device
+    I = torch.empty((M, 8), dtype=torch.int32, device=dev)
+    D = torch.empty((M, 8), dtype=torch.float32, device=dev)
+    nn = torch.empty((M,), dtype=torch.int32, device=dev)
+    if M:
+        L.check(lib.psl_knn_query(C.byref(grid.struct), L.ptr(pos), M, L.ptr(r2), float(np.float32(radius ** 2)),
+                                  int(group), L.ptr(I), L.ptr(D), L.ptr(nn), L.stream()), 'psl_knn_query')
+    return D, I, nn
+
+
+class _CompositeFn(torch.autograd.Function):
+    """raw2outputs_nerf_color (common.py:298-336); `has_nb` carries the Renderer.py:189-190 masking."""
+
+    @staticmethod
+    def forward(ctx, raw, z_vals, has_nb, coef):
+        lib = L.load()
+        R, S = z_vals.shape
+        dev = raw.device
+        rawc, zc = _f32c(raw).reshape(R * S, 4), _f32c(z_vals)
+        hb = has_nb.to(torch.uint8).contiguous() if has_nb is not None else torch.ones(R * S, dtype=torch.uint8, device=dev)
+        depth = torch.empty((R,), dtype=torch.float32, device=dev)
+        var = torch.empty((R,), dtype=torch.float32, device=dev)
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        w = torch.empty((R, S), dtype=torch.float32, device=dev)
+        L.check(lib.psl_composite_fwd(L.ptr(rawc), L.ptr(hb), L.ptr(zc), R, S, float(coef), L.ptr(depth), L.ptr(var),
+                                      L.ptr(rgb), L.ptr(w), L.stream()), 'psl_composite_fwd')
+        ctx.save_for_backward(rawc, zc, hb)
+        ctx.coef = float(coef)
+        ctx.mark_non_differentiable(w)
+        return depth, var, rgb, w
+
+    @staticmethod
+    def backward(ctx, d_depth, d_var, d_rgb, _dw):
+        lib = L.load()
+        rawc, zc, hb = ctx.saved_tensors
+        R, S = zc.shape
+        d_raw = torch.empty_like(rawc)
+        L.check(lib.psl_composite_bwd(L.ptr(rawc), L.ptr(hb), L.ptr(zc), R, S, ctx.coef,
+                                      L.ptr(_f32c(d_depth)) if d_depth is not None else None,
+                                      L.ptr(_f32c(d_var)) if d_var is not None else None,
+                                      L.ptr(_f32c(d_rgb)) if d_rgb is not None else None, L.ptr(d_raw), L.stream()),
+                'psl_composite_bwd')
+        return d_raw.reshape(R, S, 4), None, None, None
+
+
+def render(st: RenderSettings, grid: SpatialHash, params: Sequence[torch.Tensor], rays_o, rays_d, gt_depth,
+           cloud_pos, geo_feats, col_feats, r2_ray=None, z_override=None, rand_geo=None, rand_col=None, affine=None):
+    """Fused render_batch_ray core.  -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) bool."""
+    dev = rays_o.device
+    if rand_geo is None:
+        rand_geo = torch.zeros(32, device=dev)
+    if rand_col is None:
+        rand_col = torch.zeros(32, device=dev)
+    return _RenderFn.apply(st, grid, _f32c(gt_depth).reshape(-1), z_override, r2_ray, _f32c(rand_geo), _f32c(rand_col),
+                           cloud_pos, rays_o, rays_d, geo_feats, col_feats, affine, *params)
+
+
+def decode(st: RenderSettings, grid: SpatialHash, params, p, cloud_pos, geo_feats, col_feats, r2_pts=None, r2_group=1,
+           rand_geo=None, rand_col=None, affine=None):
+    dev = p.device
+    if rand_geo is None:
+        rand_geo = torch.zeros(32, device=dev)
+    if rand_col is None:
+        rand_col = torch.zeros(32, device=dev)
+    return _DecodeFn.apply(st, grid, r2_pts, int(r2_group), _f32c(rand_geo), _f32c(rand_col), cloud_pos, p, geo_feats,
+                           col_feats, affine, *params)
+
+
+def composite(raw, z_vals, has_nb=None, coef=0.1):
+    return _CompositeFn.apply(raw, z_vals, has_nb, coef)

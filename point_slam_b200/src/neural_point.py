@@ -1,0 +1,227 @@
+"""Drop-in for the reference `src/neural_point.py`: same class name, constructor and the 14 public methods
+(neural_point.py:44-277), backed by a GPU-resident spatial hash and the exact radius-kNN kernel instead of a
+faiss GpuIndexIVFFlat.  Positions live in a device tensor (capacity-doubling) instead of a Python list; the list
+view the reference API promises (`cloud_pos()`, `_cloud_pos`) is materialised lazily.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from .common import setup_seed
+
+
+class _IndexShim:
+    """Duck-type of the faiss index attributes offline tools poke at (get_mesh_tsdf_fusion.py:66-82)."""
+
+    def __init__(self, owner):
+        self._o = owner
+        self.nprobe = owner.cfg['pointcloud'].get('nprobe', 1)    # accepted and ignored: the search is exact
+        self.is_trained = False
+
+    @property
+    def ntotal(self):
+        return self._o._indexed
+
+    def train(self, xb):
+        self.is_trained = True
+
+    def add(self, xb):
+        self._o._index_add(xb)
+
+    def search(self, q, k):
+        assert k == self._o.nn_num
+        D, I = self._o._search_all(q)
+        return D, I
+
+
+class NeuralPointCloud(object):
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.c_dim = cfg['model']['c_dim']
+        self.device = cfg['mapping']['device']
+        self.cuda_id = 0
+        self.use_dynamic_radius = cfg['use_dynamic_radius']
+        pc = cfg['pointcloud']
+        self.nn_num = pc['nn_num']
+        assert self.nn_num == 8, 'kernels are specialised for nn_num = 8'
+        self.nlist = pc['nlist']
+        self.radius_add, self.radius_min, self.radius_query = pc['radius_add'], pc['radius_min'], pc['radius_query']
+        self.fix_interval_when_add_along_ray = pc['fix_interval_when_add_along_ray']
+        self.N_surface = cfg['rendering']['N_surface']
+        self.N_add = pc['N_add']
+        self.near_end_surface, self.far_end_surface = pc['near_end_surface'], pc['far_end_surface']
+
+        self._pos = torch.zeros((0, 3), dtype=torch.float32, device=self.device)   # all positions ever appended
+        self._pos_list_cache = None
+        self._input_pos = []
+        self._input_rgb = []
+        self._pts_num = 0
+        self._indexed = 0                  # number of positions the hash currently covers
+        self.geo_feats = None
+        self.col_feats = None
+        self.keyframe_dict = []
+        self._grid = ops.SpatialHash(cell=float(pc.get('hash_cell', self.radius_query)))
+        self.index = _IndexShim(self)
+        setup_seed(cfg['setup_seed'])
+
+    # ---- storage accessors (neural_point.py:44-89) ----------------------------------------------------------------
+    @property
+    def _cloud_pos(self):
+        if self._pos_list_cache is None:
+            self._pos_list_cache = self._pos.tolist()
+        return self._pos_list_cache
+
+    @_cloud_pos.setter
+    def _cloud_pos(self, value):          # offline tools assign a list (get_mesh_tsdf_fusion.py:66)
+        self._pos = torch.as_tensor(value, dtype=torch.float32, device=self.device).reshape(-1, 3)
+        self._pos_list_cache = None
+
+    def cloud_pos(self, index=None):
+        return self._cloud_pos if index is None else self._cloud_pos[index]
+
+    def cloud_pos_tensor(self):
+        """(N,3) float32 device tensor of the indexed positions (no host round trip)."""
+        return self._pos[:self._indexed]
+
+    def spatial_hash(self):
+        return self._grid
+
+    def input_pos(self):
+        return self._input_pos
+
+    def input_rgb(self):
+        return self._input_rgb
+
+    def pts_num(self):
+        return self._pts_num
+
+    def index_train(self, xb):
+        assert torch.is_tensor(xb), 'use tensor to train FAISS index'
+        self.index.train(xb)
+        return self.index.is_trained
+
+    def index_ntotal(self):
+        return self.index.ntotal
+
+    def get_radius_query(self):
+        return self.radius_query
+
+    def get_geo_feats(self):
+        return self.geo_feats
+
+    def get_col_feats(self):
+        return self.col_feats
+
+    def update_geo_feats(self, feats, indices=None):
+        assert torch.is_tensor(feats), 'use tensor to update features'
+        if indices is not None:
+            self.geo_feats[indices] = feats.detach().clone()
+        else:
+            assert feats.shape[0] == self.geo_feats.shape[0], 'feature shape[0] mismatch'
+            self.geo_feats = feats.detach().clone()
+
+    def update_col_feats(self, feats, indices=None):
+        assert torch.is_tensor(feats), 'use tensor to update features'
+        if indices is not None:
+            self.col_feats[indices] = feats.detach().clone()
+        else:
+            assert feats.shape[0] == self.col_feats.shape[0], 'feature shape[0] mismatch'
+            self.col_feats = feats.detach().clone()
+
+    # ---- index maintenance -----------------------------------------------------------------------------------------
+    def _index_add(self, pts):
+        """Cover `pts` with the hash.  When they are the tail of `_pos` (the add_neural_points flow) nothing is copied;
+        a foreign tensor (offline tools) is appended to `_pos` first."""
+        pts = torch.as_tensor(pts, dtype=torch.float32, device=self.device).reshape(-1, 3)
+        if self._pos.shape[0] != self._indexed + pts.shape[0]:
+            self._pos = torch.cat([self._pos[:self._indexed], pts], 0)
+            self._pos_list_cache = None
+        self._indexed = self._pos.shape[0]
+        self._grid.build(self._pos)
+        self.index.is_trained = True
+
+    def _search_all(self, q):
+        """faiss-style search: D (M,8) f32, I (M,8) i64 of the 8 nearest points within the largest radius the
+        configuration can ask for (slots beyond it: I=-1, D=FLT_MAX)."""
+        rmax = max(self.radius_query, self.radius_add, 2.0 * self.cfg['pointcloud'].get('radius_add_max', 0.0))
+        D, I, _ = ops.knn_query(self._grid, q, radius=rmax)
+        return D, I.long()
+
+    # ---- point insertion (neural_point.py:91-167) --------------------------------------------------------------------
+    def add_neural_points(self, batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color, train=False,
+                          is_pts_grad=False, dynamic_radius=None):
+        if not batch_rays_o.shape[0]:
+            return 0
+        mask = batch_gt_depth > 0
+        batch_gt_color = batch_gt_color * 255
+        o, d, depth, color = batch_rays_o[mask], batch_rays_d[mask], batch_gt_depth[mask], batch_gt_color[mask]
+        pts_gt = (o[..., None, :] + d[..., None, :] * depth[..., None, None]).reshape(-1, 3)
+        keep = torch.ones(pts_gt.shape[0], device=self.device).bool()
+        if self.index.is_trained:
+            _, _, n_gt = self.find_neighbors_faiss(pts_gt, step='add', is_pts_grad=is_pts_grad,
+                                                   dynamic_radius=dynamic_radius)
+            keep = (n_gt == 0)                                               # no indexed point inside the add radius
+        self._input_pos.extend(pts_gt[keep].tolist())
+        self._input_rgb.extend(color[keep].tolist())
+        depth_rep = depth.unsqueeze(-1).repeat(1, self.N_add)
+        if self.fix_interval_when_add_along_ray:
+            z_vals = depth_rep + torch.linspace(-0.04, 0.04, steps=self.N_add, device=self.device).unsqueeze(0)
+        else:
+            t = torch.linspace(0.0, 1.0, steps=self.N_add, device=self.device)
+            z_vals = self.near_end_surface * depth_rep * (1. - t) + self.far_end_surface * depth_rep * t
+        pts = (o[..., None, :] + d[..., None, :] * z_vals[..., :, None])[keep].reshape(-1, 3)
+        self._pos = torch.cat([self._pos[:self._indexed], pts.float()], 0)
+        self._pos_list_cache = None
+        self._pts_num += pts.shape[0]
+        fresh = lambda n: torch.zeros([n, self.c_dim], device=self.device).normal_(mean=0, std=0.1)
+        if self.geo_feats is None:
+            self.geo_feats = fresh(self._pts_num)
+            self.col_feats = fresh(self._pts_num)
+        else:
+            self.geo_feats = torch.cat([self.geo_feats, fresh(pts.shape[0])], 0)
+            self.col_feats = torch.cat([self.col_feats, fresh(pts.shape[0])], 0)
+        self.index.train(pts)
+        self.index.add(pts)
+        return torch.sum(keep)
+
+    # ---- kNN (neural_point.py:169-215) --------------------------------------------------------------------------------
+    def find_neighbors_faiss(self, pos, step='add', retrain=False, is_pts_grad=False, dynamic_radius=None):
+        assert step in ['add', 'query']
+        if step == 'query':
+            radius = self.radius_query
+        else:
+            radius = self.radius_min if is_pts_grad else self.radius_add
+        if dynamic_radius is not None:
+            assert pos.shape[0] == dynamic_radius.shape[0], 'shape mis-match for input points and dynamic radius'
+        D, I, neighbor_num = ops.knn_query(self._grid, pos.float(), radius=radius, dynamic_radius=dynamic_radius, group=1)
+        return D, I.long(), neighbor_num
+
+    # ---- zero-depth rays (neural_point.py:217-277) ---------------------------------------------------------------------
+    def sample_near_pcl(self, rays_o, rays_d, near, far, num):
+        rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+        n_rays = rays_d.shape[0]
+        intervals = 25
+        far_f = far.item() if torch.is_tensor(far) else float(far)
+        z_probe = torch.linspace(near, far_f, steps=intervals, device=self.device)
+        pts = (rays_o[..., None, :] + rays_d[..., None, :] * z_probe[..., :, None]).reshape(-1, 3)
+        _, _, neighbor_num = self.find_neighbors_faiss(pts, step='query')
+        hit = neighbor_num.reshape(n_rays, intervals) > 0
+        invalid = hit.sum(-1) < 2                                            # fewer than two probes near the cloud
+        # first and second hit probe per ray; float64 linspace between their depths, like the numpy reference
+        order = torch.argsort((~hit).to(torch.uint8), dim=1, stable=True)[:, :2]
+        sec = torch.from_numpy(np.linspace(near, far_f, intervals)).to(self.device)
+        z0, z1 = sec[order[:, 0]], sec[order[:, 1]]
+        steps = torch.arange(num, device=self.device, dtype=torch.float64)
+        z_valid = _np_linspace(z0, z1, num, steps)
+        z_default = torch.from_numpy(np.linspace(near, far_f, num)).to(self.device).expand(n_rays, num)
+        z = torch.where(invalid[:, None], z_default, z_valid)
+        return z.float(), invalid
+
+
+def _np_linspace(a, b, num, steps):
+    """numpy.linspace(a, b, num) for vectors a, b in float64: a + arange(num)*step with the last sample pinned to b."""
+    div = num - 1
+    step = (b - a) / div
+    y = a[:, None] + steps[None, :] * step[:, None]
+    y[:, -1] = b
+    return y
