@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- Point-SLAM render hot path on B200: ray-samples/sec (render + kNN + MLP), frames/sec.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # CUDA path (this repo)
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host cores (CPU oracle port)
+
+One STEP = the hot-path work the reference does for one Replica-config frame:
+40 tracking iterations x 1500 rays (render fwd + loss + bwd to the 7-d pose + Adam) and the per-frame share of
+mapping, 300/5 = 60 iterations x 5000 rays over the current frame + 4 keyframes (first 40 % geometry stage, then colour;
+bwd to the frustum-selected feature slices and the colour decoder + Adam), S = 5 samples per ray, against a
+replicated synthetic 500k-point neural point cloud, 640x480 synthetic RGB-D frames (point_slam_b200/synth.py).
+`value` = ray-samples through render fwd+bwd per second with the frame already in HBM; `e2e` = the same step fed
+from pinned HOST memory (frame colour/depth/radius map H2D, pose + loss D2H inside the timed region).
+Multi-GPU (`--gpus N`, torchrun): one independent scene per GPU (BASELINE config C5, the reference's SLURM array),
+no data-path collective -> weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from point_slam_b200 import synth                                    # noqa: E402
+from point_slam_b200.default_config import make_cfg                  # noqa: E402
+from point_slam_b200 import iteration as IT                          # noqa: E402
+
+INTR = synth.TUM_INTRINSICS
+S = 5
+TRACK_ITERS, TRACK_PIX = 40, 1500            # configs/Replica/replica.yaml:7-8
+MAP_ITERS, MAP_PIX = 60, 5000                # 300 iterations every 5th frame (replica.yaml:15,17; point_slam.yaml:42)
+GEO_ITERS = int(MAP_ITERS * 0.4)             # mapping.geo_iter_ratio (point_slam.yaml:41)
+N_KEYFRAMES = 4
+ALGO_BYTES_FWD = 2144 + 49.0 / S             # gathered bytes per sample, colour stage forward
+ALGO_BYTES_BWD = 2144 + 2048 + 49.0 / S      # + feature-gradient writes before dedup
+FLOP_FWD = 397894                            # SURVEY.md section 8d (encode_rel_pos_in_col=True)
+
+
+def load_decoder_state():
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'decoders_base.npz'))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def make_frames(n, seed):
+    poses = synth.trajectory(n, seed=seed)
+    frames = []
+    for k in range(n):
+        depth, color = synth.make_frame(poses[k], INTR)
+        _, rq = synth.sobel_radius_map(color)
+        frames.append(dict(c2w=poses[k], depth=depth, color=color, dyn_r_query=rq))
+    return frames
+
+
+def cam_tensor_from_c2w(c2w, jitter, rng):
+    from scipy.spatial.transform import Rotation
+    q = np.roll(Rotation.from_matrix(c2w[:3, :3]).as_quat(), 1)
+    t = c2w[:3, 3] + rng.normal(0, jitter, 3)
+    return torch.tensor(np.concatenate([q, t]), dtype=torch.float32)
+
+
+class Clocks:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(',') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if 'Active' in v and 'Not' not in v:
+                    reasons.add(name)
+        hi = sorted(sm)[len(sm) // 2:] if sm else []          # upper half == samples taken under load
+        return {'sm_mhz': float(np.median(hi)) if hi else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------------------
+class GpuScene:
+    def __init__(self, rank, device, n_points, n_frames):
+        from point_slam_b200.src.conv_onet import config as model_config
+        from point_slam_b200.src.neural_point import NeuralPointCloud
+        from point_slam_b200.src.utils.Renderer import Renderer
+        import types
+        self.device = device
+        self.cfg = make_cfg('replica', device)
+        torch.manual_seed(1219)
+        self.decoders = model_config.get_model(self.cfg)
+        sd = load_decoder_state()
+        emb = sd.pop('color_decoder.embedder._B')
+        self.decoders.load_state_dict(sd, strict=True)
+        self.decoders.color_decoder.embedder._B = emb
+        self.decoders = self.decoders.to(device)
+        cloud = synth.make_cloud(n_points, seed=1219 + rank)
+        gf, cf = synth.make_features(n_points, seed=1219 + rank)
+        self.npc = NeuralPointCloud(self.cfg)
+        self.npc._cloud_pos = torch.from_numpy(cloud)
+        self.npc._pts_num = n_points
+        self.npc.geo_feats = torch.from_numpy(gf).to(device)
+        self.npc.col_feats = torch.from_numpy(cf).to(device)
+        self.npc.index.add(self.npc._pos)
+        self.renderer = Renderer(self.cfg, None, types.SimpleNamespace(**{k: INTR[k] for k in ('H', 'W', 'fx', 'fy', 'cx', 'cy')}))
+        self.renderer.sigmoid_coefficient = 0.1
+        self.frames_host = make_frames(n_frames + N_KEYFRAMES, seed=1219 + rank)
+        self.rng = np.random.default_rng(7 + rank)
+        # keyframes are resident (they were mapped earlier); incoming frames live in pinned host memory
+        self.keyframes = [self._to_device(f) for f in self.frames_host[:N_KEYFRAMES]]
+        self.pinned = [{k: torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory() for k in ('color', 'depth', 'dyn_r_query')}
+                       for f in self.frames_host[N_KEYFRAMES:]]
+        self.resident = [self._to_device(f) for f in self.frames_host[N_KEYFRAMES:]]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
+        self.out_host = torch.empty(8, dtype=torch.float32).pin_memory()
+
+    def _to_device(self, f):
+        d = self.device
+        return dict(color=torch.from_numpy(f['color']).to(d), depth=torch.from_numpy(f['depth']).to(d),
+                    dyn_r_query=torch.from_numpy(f['dyn_r_query']).to(d),
+                    c2w=torch.from_numpy(f['c2w'][:3, :4].astype(np.float32)).to(d))
+
+    def step(self, k, from_host):
+        """Process frame k.  Returns the number of ray-samples rendered (fwd+bwd)."""
+        d = self.device
+        fh = self.frames_host[N_KEYFRAMES + k]
+        if from_host:
+            cur = {n: t.to(d, non_blocking=True) for n, t in self.pinned[k].items()}
+            cur['c2w'] = torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d)
+        else:
+            cur = self.resident[k]
+        npc, dec, render = self.npc, self.decoders, self.renderer.render_batch_ray
+        cloud = npc.cloud_pos_tensor()
+        samples = 0
+        # ---- tracking: Adam on [quat, T] (Tracker.py:283-332, separate_LR off for brevity) -------------------------
+        cam = cam_tensor_from_c2w(fh['c2w'], 0.01, self.rng).to(d).requires_grad_(True)
+        opt = torch.optim.Adam([cam], lr=0.002)
+        geo, col = npc.get_geo_feats(), npc.get_col_feats()
+        loss = None
+        for _ in range(TRACK_ITERS):
+            loss, n = IT.tracker_iteration(render, npc, dec, cam, opt, cur['color'], cur['depth'], cur['dyn_r_query'], INTR,
+                                           TRACK_PIX, d, geo, col, cloud, edge=(100, 100))
+            samples += n * S
+        # ---- mapping: features in the current frustum + colour decoder ------------------------------------------------
+        idx = IT.frustum_indices(cloud, cur['c2w'], INTR)
+        state = IT.MapperState(npc, dec, idx)
+        kfs = [cur] + self.keyframes
+        for it in range(MAP_ITERS):
+            loss, n = IT.mapper_iteration(render, npc, dec, state, kfs, INTR, MAP_PIX, d,
+                                          'geometry' if it < GEO_ITERS else 'color', cloud)
+            samples += n * S
+        if from_host:
+            self.out_host[:7].copy_(cam.detach(), non_blocking=True)
+            self.out_host[7:8].copy_(loss.reshape(1), non_blocking=True)
+        return samples
+
+
+def timed_steps(scene, steps, first, from_host, dist):
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    samples = 0
+    for k in range(steps):
+        samples += scene.step(first + k, from_host)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1), samples
+
+
+def run_ours(args):
+    from point_slam_b200 import _lib
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    dist = None
+    torch.cuda.set_device(local)
+    device = f'cuda:{local}'
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    lib = _lib.load()
+    scene = GpuScene(rank, device, args.points, args.steps + args.warmup)
+    for k in range(args.warmup):
+        scene.step(k, False)
+    clocks = Clocks(local) if rank == 0 else None
+    l0 = lib.psl_launch_count()
+    ms, samples = timed_steps(scene, args.steps, args.warmup, False, dist)
+    launches = lib.psl_launch_count() - l0
+    ms_e2e, samples_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
+    clk = clocks.stop() if clocks else None
+    # per-kernel device time of one more step (CUDA events on the launching stream inside the library)
+    _lib.timing_enable(True)
+    n_prof = scene.step(args.warmup, False)
+    prof = _lib.timing_collect()
+    _lib.timing_enable(False)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([samples, samples_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        samples, samples_e2e = float(s[0]), float(s[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = samples / (ms * 1e-3)
+    e2e = samples_e2e / (ms_e2e * 1e-3)
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    tot_kernel_ms = sum(v[0] for v in prof.values())
+    top = max(prof, key=lambda k: prof[k][0])
+    top_ms, top_n = prof[top]
+    # samples one launch of the dominant kernel processes: tracker launches see ~TRACK_PIX*S, mapper ~MAP_PIX*S
+    per_launch_samples = n_prof / max(prof['decode_fwd'][1], 1)
+    bytes_per_sample = ALGO_BYTES_BWD if top == 'decode_bwd' else ALGO_BYTES_FWD
+    achieved = per_launch_samples * bytes_per_sample / (top_ms / max(top_n, 1) * 1e-3) / 1e9
+    traffic = None
+    tj = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tj):
+        traffic = json.load(open(tj)).get(top)
+    out = {
+        'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': value, 'unit': 'samples/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'frames_per_sec': world * args.steps / (ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'C2 Replica-office0-like frame: 40 track it x 1500 rays + 60 map it x 5000 rays, S=5, '
+                               f'{args.points} pts, 640x480; one scene per GPU', 'points': args.points,
+                   'work_per_step': 'fwd + loss + bwd + Adam (tracker pose; mapper features + colour decoder)',
+                   'l2': 'inputs larger than L2 (cloud+features 134 MB, saved activations ~290 MB / mapper iteration)',
+                   'parallelism': f'scene-per-gpu x{world}'},
+        'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes, 'd2h_bytes_per_step': 32,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches),
+        'clocks': clk,
+        'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_sample': bytes_per_sample, 'samples_per_launch': per_launch_samples,
+                     'avg_launch_ms': top_ms / max(top_n, 1),
+                     'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
+                     'fp32_tflops_fwd_bwd': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12},
+        'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
+        'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline_sample(args.points)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm (CPU oracle port) on the host cores, same iteration shells
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuScene:
+    def __init__(self, n_points, n_frames):
+        from scipy.spatial import cKDTree
+        from point_slam_b200.src.conv_onet import config as model_config
+        self.cfg = make_cfg('replica', 'cpu')
+        torch.manual_seed(1219)
+        self.decoders = model_config.get_model(self.cfg)
+        sd = load_decoder_state()
+        emb = sd.pop('color_decoder.embedder._B')
+        self.decoders.load_state_dict(sd, strict=True)
+        self.decoders.color_decoder.embedder._B = emb
+        cloud = synth.make_cloud(n_points, seed=1219)
+        gf, cf = synth.make_features(n_points, seed=1219)
+        self.cloud = torch.from_numpy(cloud)
+        self.geo, self.col = torch.from_numpy(gf), torch.from_numpy(cf)
+        self.tree = cKDTree(cloud.astype(np.float64))
+        self.frames = []
+        for f in make_frames(n_frames + 1, seed=1219):
+            self.frames.append(dict(color=torch.from_numpy(f['color']), depth=torch.from_numpy(f['depth']),
+                                    dyn_r_query=torch.from_numpy(f['dyn_r_query']),
+                                    c2w=torch.from_numpy(f['c2w'][:3, :4].astype(np.float32)), c2w64=f['c2w']))
+        self.rng = np.random.default_rng(7)
+
+    # duck-typed npc for the iteration shells
+    def get_geo_feats(self):
+        return self.geo
+
+    def get_col_feats(self):
+        return self.col
+
+    def render(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None, npc_geo_feats=None, npc_col_feats=None,
+               is_tracker=False, cloud_pos=None, dynamic_r_query=None, exposure_feat=None):
+        from oracle import point_slam_oracle as O
+        P = dict(decoders.named_parameters())
+        P['color_decoder.embedder._B'] = decoders.color_decoder.embedder._B
+        rg = torch.zeros([32]).normal_(mean=0, std=0.01)
+        rc = torch.zeros([32]).normal_(mean=0, std=0.01)
+        return O.render_batch_ray(P, rays_d, rays_o, gt_depth, stage, self.cloud, npc_geo_feats, npc_col_feats, S=S,
+                                  is_tracker=is_tracker, radius_query=0.08, dynamic_r_query=dynamic_r_query, rand_geo=rg,
+                                  rand_col=rc, coef=0.1, encode_rel_pos=True, tree=self.tree)
+
+    def step(self, k, track_iters, map_iters, map_pix):
+        cur = self.frames[1 + k]
+        samples = 0
+        cam = cam_tensor_from_c2w(cur['c2w64'], 0.01, self.rng).requires_grad_(True)
+        opt = torch.optim.Adam([cam], lr=0.002)
+        for _ in range(track_iters):
+            _, n = IT.tracker_iteration(self.render, self, self.decoders, cam, opt, cur['color'], cur['depth'],
+                                        cur['dyn_r_query'], INTR, TRACK_PIX, 'cpu', self.geo, self.col, self.cloud,
+                                        edge=(100, 100))
+            samples += n * S
+        idx = IT.frustum_indices(self.cloud, cur['c2w'], INTR)
+        state = IT.MapperState(self, self.decoders, idx)
+        for it in range(map_iters):
+            _, n = IT.mapper_iteration(self.render, self, self.decoders, state, [cur, self.frames[0]], INTR, map_pix, 'cpu',
+                                       'color', self.cloud)
+            samples += n * S
+        return samples
+
+
+def cpu_baseline_sample(n_points):
+    """Bounded sample of the same workload on the host cores: 1 tracking iteration (1500 rays) + 1 mapping iteration
+    (2000 rays, colour stage), after one untimed warm-up of the same."""
+    torch.set_num_threads(os.cpu_count())
+    sc = CpuScene(n_points, 2)
+    sc.step(0, 1, 1, 2000)
+    t0 = time.perf_counter()
+    n = sc.step(1, 1, 1, 2000)
+    dt = time.perf_counter() - t0
+    return {'value': n / dt, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': f'1 tracking iteration x 1500 rays + 1 mapping iteration x 2000 rays (colour stage), fwd+loss+bwd+Adam, '
+                      f'{n_points}-point cloud, S=5, torch {torch.__version__} CPU + scipy cKDTree exact kNN; {dt:.1f} s',
+            'seconds': dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    sc = CpuScene(args.points, args.steps + args.warmup)
+    for k in range(args.warmup):
+        sc.step(k, 1, 1, 1000)
+    t0 = time.perf_counter()
+    samples = 0
+    for k in range(args.steps):
+        samples += sc.step(args.warmup + k, 1, 1, 1000)
+    dt = time.perf_counter() - t0
+    v = samples / dt
+    out = {'impl': 'reference', 'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': v,
+           'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': dt * 1e3 / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'C2 Replica-office0-like frame (same scene/frames as the CUDA arm); each step is a bounded '
+                                  'sample: 1 tracking iteration x 1500 rays + 1 mapping iteration x 1000 rays',
+                      'points': args.points},
+           'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                            'sample': 'per step: 1 tracking iteration x 1500 rays + 1 mapping iteration x 1000 rays, '
+                                      'fwd+loss+bwd+Adam on the host cores (oracle port of the reference, exact cKDTree kNN)'},
+           'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--points', type=int, default=500000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        assert torch.cuda.is_available(), 'bench.py (CUDA arm) needs a GPU; there is no CPU fallback'
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

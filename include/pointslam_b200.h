@@ -44,6 +44,15 @@ int psl_version(void);
 const char* psl_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int psl_device_sm_count(void);
+/* optional device timing: when enabled, every kernel launch made by the library is bracketed by CUDA events on the
+ * launching stream; psl_timing_collect synchronises the device and returns summed milliseconds / launch counts per
+ * kernel family: 0 knn, 1 decode_fwd, 2 decode_bwd, 3 composite/ray kernels, 4 feature scatter, 5 param pack,
+ * 6 partial-gradient reduce (arrays of PSL_TIMING_SLOTS entries). */
+#define PSL_TIMING_SLOTS 7
+/* kernels launched by this process through the library so far (bench.py's gpu_launches) */
+unsigned long long psl_launch_count(void);
+int psl_timing_enable(int on);
+int psl_timing_collect(float* ms_out_host, int* count_out_host);
 
 /* ------------------------------------------------------------------------- *
  * K0  spatial hash of the neural point cloud

@@ -51,6 +51,9 @@ _SIGS = {
     'psl_version': (C.c_int, []),
     'psl_last_error': (C.c_char_p, []),
     'psl_device_sm_count': (C.c_int, []),
+    'psl_launch_count': (C.c_uint64, []),
+    'psl_timing_enable': (C.c_int, [C.c_int]),
+    'psl_timing_collect': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     'psl_grid_sort_ws_bytes': (_sz, [_i64]),
     'psl_grid_sort': (C.c_int, [_vp, _i64, _f32, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
     'psl_grid_hash': (C.c_int, [_vp, _i64, _vp, _vp, C.c_uint32, _vp]),
@@ -133,6 +136,21 @@ def ptr(t, dtype=None):
     if dtype is not None:
         assert t.dtype == dtype, f'expected {dtype}, got {t.dtype}'
     return C.c_void_p(t.data_ptr())
+
+
+TIMING_NAMES = ['knn', 'decode_fwd', 'decode_bwd', 'composite', 'scatter', 'pack', 'reduce']
+
+
+def timing_enable(on: bool):
+    load().psl_timing_enable(int(on))
+
+
+def timing_collect():
+    """-> {name: (total_ms, launches)} since the last enable/collect (synchronises the device)."""
+    ms = (C.c_float * len(TIMING_NAMES))()
+    cnt = (C.c_int * len(TIMING_NAMES))()
+    check(load().psl_timing_collect(ms, cnt), 'psl_timing_collect')
+    return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(TIMING_NAMES)}
 
 
 def stream():

@@ -33,6 +33,15 @@ inline cudaStream_t as_stream(psl_stream_t s) { return reinterpret_cast<cudaStre
 
 int sm_count();
 
+// optional per-kernel device timing (psl_timing_enable): CUDA events recorded on the launching stream
+enum { T_KNN = 0, T_DECODE_FWD = 1, T_DECODE_BWD = 2, T_COMPOSITE = 3, T_SCATTER = 4, T_PACK = 5, T_REDUCE = 6, T_COUNT = 7 };
+struct TimingScope {
+    int slot;
+    cudaStream_t st;
+    TimingScope(int id, cudaStream_t s, int n_kernels = 1);
+    ~TimingScope();
+};
+
 constexpr float kTwoPi = 6.283185307179586f;    // float32(2*math.pi), decoder.py:33
 constexpr uint64_t kEmptyKey = ~0ull;
 

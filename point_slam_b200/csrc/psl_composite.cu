@@ -160,6 +160,7 @@ extern "C" int psl_composite_fwd(const float* raw, const uint8_t* has_nb, const 
                                  psl_stream_t stream) {
     PSL_REQUIRE(raw && has_nb && z_vals && depth && var && rgb, "NULL argument");
     if (n_rays == 0) return 0;
+    TimingScope ts(T_COMPOSITE, as_stream(stream));
     k_composite_fwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(raw), has_nb, z_vals,
                                                                      n_rays, n_samples, coef, depth, var, rgb, weights);
     PSL_CHECK_CUDA(cudaGetLastError());
@@ -172,6 +173,7 @@ extern "C" int psl_composite_bwd(const float* raw, const uint8_t* has_nb, const 
     PSL_REQUIRE(raw && has_nb && z_vals && d_raw, "NULL argument");
     PSL_REQUIRE(n_samples <= MAX_S, "n_samples > 64 not supported by the composite backward");
     if (n_rays == 0) return 0;
+    TimingScope ts(T_COMPOSITE, as_stream(stream));
     k_composite_bwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(raw), has_nb, z_vals,
                                                                      n_rays, n_samples, coef, d_depth, d_var, d_rgb,
                                                                      reinterpret_cast<float4*>(d_raw));
@@ -183,6 +185,7 @@ extern "C" int psl_rays_bwd(const float* d_pos, const float* z_vals, int64_t n_r
                             float* d_rays_d, psl_stream_t stream) {
     PSL_REQUIRE(d_pos && z_vals, "NULL argument");
     if (n_rays == 0) return 0;
+    TimingScope ts(T_COMPOSITE, as_stream(stream));
     k_rays_bwd<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(d_pos, z_vals, n_rays, n_samples, d_rays_o, d_rays_d);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -192,6 +195,7 @@ extern "C" int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_sam
                             uint8_t* ray_mask, psl_stream_t stream) {
     PSL_REQUIRE(has_nb && ray_mask, "NULL argument");
     if (n_rays == 0) return 0;
+    TimingScope ts(T_COMPOSITE, as_stream(stream));
     k_ray_mask<<<nblk(n_rays, 128), 128, 0, as_stream(stream)>>>(has_nb, n_rays, n_samples, min_count, ray_mask);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -224,6 +228,7 @@ extern "C" int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, c
     unsigned* v_in = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
     unsigned* v_out = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
     size_t cub_bytes = ws_bytes - (size_t)(w - static_cast<unsigned char*>(ws));
+    TimingScope ts(T_SCATTER, st, 6);   // key kernel + 4 radix-sort passes + segment kernel
     k_pair_keys<<<nblk(np, 256), 256, 0, st>>>(I, wn, np, (unsigned)n_points, k_in, v_in);
     int bits = 1;
     while ((1ll << bits) <= n_points) ++bits;

@@ -930,9 +930,12 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
         PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_BYTES));
         attr_set = true;
     }
-    PSL_CHECK_CUDA(cudaMemsetAsync(a.partial, 0, sizeof(float) * (size_t)GR_TOTAL * grid, st));
-    k_decode_bwd<<<(unsigned)grid, NWARP * 32, SM_BWD_BYTES, st>>>(a, n_tiles);
-    PSL_CHECK_CUDA(cudaGetLastError());
+    {
+        TimingScope ts(T_DECODE_BWD, st, 2);   // memset + kernel
+        PSL_CHECK_CUDA(cudaMemsetAsync(a.partial, 0, sizeof(float) * (size_t)GR_TOTAL * grid, st));
+        k_decode_bwd<<<(unsigned)grid, NWARP * 32, SM_BWD_BYTES, st>>>(a, n_tiles);
+        PSL_CHECK_CUDA(cudaGetLastError());
+    }
     if (G || d_exposure_affine) {
         ReduceJobs J;
         J.n = 0;
@@ -963,6 +966,7 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
         }
         if (color) add(d_exposure_affine, GR_aff, 12);
         if (J.n > 0) {
+            TimingScope ts(T_REDUCE, st);
             k_reduce_partials<<<dim3(16, J.n), 256, 0, st>>>(a.partial, (int)grid, J);
             PSL_CHECK_CUDA(cudaGetLastError());
         }

@@ -388,6 +388,7 @@ extern "C" int psl_pack_params(const psl_decoder_params* P, float* packed, psl_s
     add_job(J, P->c_Wo, OFF_COL(4) + CL_X(4), 4, 128, 3, 128, 0, 1);
     add_job(J, P->c_bo, OFF_COL(4) + CL_X(4) + 512, 3, 1, 3, 3, 0, 0);
     for (int i = 0; i < J.n; ++i) PSL_REQUIRE(J.j[i].src != nullptr, "NULL parameter pointer");
+    TimingScope ts(T_PACK, st);
     k_pack<<<dim3(8, J.n), 256, 0, st>>>(J, packed);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -417,6 +418,7 @@ extern "C" int psl_decode_fwd(const psl_decode_cfg* cfg, const float* packed, co
         attr_set = true;
     }
     long long blocks = n_tiles < sm_count() ? n_tiles : sm_count();
+    TimingScope ts(T_DECODE_FWD, as_stream(stream));
     if (save) k_decode_fwd<true><<<(unsigned)blocks, NWARP * 32, SM_FWD_BYTES, as_stream(stream)>>>(a, n_tiles);
     else k_decode_fwd<false><<<(unsigned)blocks, NWARP * 32, SM_FWD_BYTES, as_stream(stream)>>>(a, n_tiles);
     PSL_CHECK_CUDA(cudaGetLastError());

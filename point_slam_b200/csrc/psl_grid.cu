@@ -334,6 +334,7 @@ static int launch_knn(const GridDev& g, const KnnArgs& a, cudaStream_t st) {
     long long blocks = (n_work + KNN_WARPS - 1) / KNN_WARPS;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    TimingScope ts(T_KNN, st);
     k_knn<RAYS><<<(unsigned)blocks, KNN_WARPS * 32, smem, st>>>(g, a, n_work, n_chunks);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
