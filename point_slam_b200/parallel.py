@@ -1,0 +1,115 @@
+"""Multi-GPU plumbing for the render path: one process per GPU, the neural point cloud, its
+features and the decoders REPLICATED on every rank; units of work (scenes, frames, image rows) are sharded with no
+data-path collective.  The only exchange is the periodic map delta after a mapping step -- appended points
+(`add_neural_points`, neural_point.py:91-167), updated feature rows (`update_geo_feats/update_col_feats`,
+neural_point.py:75-89) and the colour decoder (Mapper.py:368-373 optimises it) -- broadcast from the mapping rank over
+NCCL (NVLink/NVSwitch); gloo is used by the CPU tests.  The delta is a few MB, i.e. latency bound: three broadcasts
+(header, int64 payload, float32 payload) regardless of how many tensors changed.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced [begin, end) of `n_items` for `rank` (image rows, frames, scenes)."""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_strided(n_items: int, rank: int, world: int) -> List[int]:
+    """Frames rank, rank+world, ... (keeps every rank close to the live end of the sequence)."""
+    return list(range(rank, n_items, world))
+
+
+@dataclass
+class MapDelta:
+    n_before: int                      # points before the append
+    pos_new: torch.Tensor              # (K,3) f32
+    geo_new: torch.Tensor              # (K,32) f32
+    col_new: torch.Tensor              # (K,32) f32
+    upd_idx: torch.Tensor              # (U,) i64 rows whose features changed
+    geo_upd: torch.Tensor              # (U,32)
+    col_upd: torch.Tensor              # (U,32)
+    decoder_flat: torch.Tensor         # colour-decoder parameters, flattened in `parameters()` order
+
+
+def make_delta(npc, decoders, n_before: int, upd_idx: Optional[torch.Tensor]) -> MapDelta:
+    """Collect, on the mapping rank, what changed since the cloud had `n_before` points."""
+    pos = npc.cloud_pos_tensor()
+    geo, col = npc.get_geo_feats(), npc.get_col_feats()
+    dev = geo.device
+    if upd_idx is None:
+        upd_idx = torch.zeros(0, dtype=torch.int64, device=dev)
+    upd_idx = upd_idx.to(dev).long()
+    flat = torch.cat([p.detach().reshape(-1).float() for p in decoders.color_decoder.parameters()])
+    return MapDelta(n_before, pos[n_before:].float(), geo[n_before:], col[n_before:], upd_idx, geo[upd_idx], col[upd_idx], flat)
+
+
+def broadcast_delta(delta: Optional[MapDelta], src: int, device, n_decoder_floats: int, group=None) -> MapDelta:
+    """All ranks call this; `delta` is read on `src` and returned (as received) on every rank."""
+    rank = dist.get_rank(group)
+    hdr = torch.zeros(3, dtype=torch.int64, device=device)
+    if rank == src:
+        hdr[0], hdr[1], hdr[2] = delta.n_before, delta.pos_new.shape[0], delta.upd_idx.shape[0]
+    dist.broadcast(hdr, src, group=group)
+    n_before, K, U = (int(v) for v in hdr.tolist())
+    n_f = K * 67 + U * 64 + n_decoder_floats
+    if rank == src:
+        idx = delta.upd_idx.to(device)
+        pay = torch.cat([torch.cat([delta.pos_new, delta.geo_new, delta.col_new], 1).reshape(-1),
+                         torch.cat([delta.geo_upd, delta.col_upd], 1).reshape(-1), delta.decoder_flat]).to(device).contiguous()
+        assert pay.numel() == n_f
+    else:
+        idx = torch.empty(U, dtype=torch.int64, device=device)
+        pay = torch.empty(n_f, dtype=torch.float32, device=device)
+    if U:
+        dist.broadcast(idx, src, group=group)
+    dist.broadcast(pay, src, group=group)
+    new = pay[:K * 67].reshape(K, 67)
+    upd = pay[K * 67:K * 67 + U * 64].reshape(U, 64)
+    return MapDelta(n_before, new[:, :3], new[:, 3:35], new[:, 35:], idx, upd[:, :32], upd[:, 32:], pay[K * 67 + U * 64:])
+
+
+def apply_delta(npc, decoders, d: MapDelta):
+    """Bring a replica up to date (no-op data-wise on the source rank, but cheap enough to run everywhere)."""
+    assert npc.pts_num() in (d.n_before, d.n_before + d.pos_new.shape[0]), 'replica diverged from the mapping rank'
+    if npc.pts_num() == d.n_before and d.pos_new.shape[0]:
+        npc.append_points(d.pos_new, d.geo_new, d.col_new)
+    if d.upd_idx.numel():
+        npc.update_geo_feats(d.geo_upd, d.upd_idx)
+        npc.update_col_feats(d.col_upd, d.upd_idx)
+    off = 0
+    with torch.no_grad():
+        for p in decoders.color_decoder.parameters():
+            n = p.numel()
+            p.copy_(d.decoder_flat[off:off + n].reshape(p.shape))
+            off += n
+
+
+def n_decoder_floats(decoders) -> int:
+    return sum(p.numel() for p in decoders.color_decoder.parameters())
+
+
+def render_img_sharded(render_rows, H: int, W: int, device, group=None):
+    """Row-sharded full-image render (strong scaling of Renderer.render_img, Renderer.py:204-283).
+    `render_rows(r0, r1)` -> depth (r1-r0, W), uncertainty (r1-r0, W), color (r1-r0, W, 3) for image rows [r0, r1).
+    Every rank returns the full (H,W) images; the exchange is one all_gather of 5 floats per pixel."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r0, r1 = shard_range(H, rank, world)
+    rows_max = (H + world - 1) // world
+    buf = torch.zeros(rows_max, W, 5, dtype=torch.float32, device=device)
+    if r1 > r0:
+        d, u, c = render_rows(r0, r1)
+        buf[:r1 - r0, :, 0], buf[:r1 - r0, :, 1], buf[:r1 - r0, :, 2:] = d.float(), u.float(), c.float()
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = []
+    for r in range(world):
+        a, b = shard_range(H, r, world)
+        parts.append(out[r][:b - a])
+    full = torch.cat(parts, 0)
+    return full[..., 0], full[..., 1], full[..., 2:]

@@ -184,6 +184,19 @@ class NeuralPointCloud(object):
         self.index.add(pts)
         return torch.sum(keep)
 
+    def append_points(self, pts, geo_rows, col_rows):
+        """Replica-side append: positions + their feature rows as produced by the mapping rank's add_neural_points
+        (used by point_slam_b200.parallel.apply_delta; no RNG is consumed here)."""
+        pts = pts.to(self.device).float().reshape(-1, 3)
+        self._pos = torch.cat([self._pos[:self._indexed], pts], 0)
+        self._pos_list_cache = None
+        self._pts_num += pts.shape[0]
+        g, c = geo_rows.to(self.device), col_rows.to(self.device)
+        self.geo_feats = g.clone() if self.geo_feats is None else torch.cat([self.geo_feats, g], 0)
+        self.col_feats = c.clone() if self.col_feats is None else torch.cat([self.col_feats, c], 0)
+        self.index.train(pts)
+        self.index.add(pts)
+
     # ---- kNN (neural_point.py:169-215) --------------------------------------------------------------------------------
     def find_neighbors_faiss(self, pos, step='add', retrain=False, is_pts_grad=False, dynamic_radius=None):
         assert step in ['add', 'query']
