@@ -204,6 +204,22 @@ int psl_rays_bwd(const float* d_pos, const float* z_vals, int64_t n_rays, int32_
 int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_samples, int32_t min_count, uint8_t* ray_mask,
                  psl_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * tensor-core (tcgen05, 3xTF32, TMEM-resident activations) colour branch, inference forward.
+ * psl_tc_pack_params folds fc_c into the next layer and lays the weights out as canonical K-major tf32 hi/lo chunk
+ * images (blob: psl_tc_blob_floats() floats).  psl_color_fwd_tc writes raw[:, 0:3]; raw[:, 3] and has_nb come from
+ * psl_decode_fwd(stage = PSL_STAGE_GEOMETRY) on the same kNN result.  Same reference lines as psl_decode_fwd.
+ * ------------------------------------------------------------------------- */
+size_t psl_tc_blob_floats(void);
+int psl_tc_pack_params(const psl_decoder_params* params_host, float* tc_blob, psl_stream_t stream);
+int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
+                     const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos,
+                     const float* col_feats, const float* rand_col, const float* exposure_affine, float* raw,
+                     psl_stream_t stream);
+
+/* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
+int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

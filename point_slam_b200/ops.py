@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -175,6 +176,17 @@ class RenderSettings:
                            self.min_nn, int(r2_group), int(self.is_tracker), 0, float(r2_scalar))
 
 
+USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch for inference (no-grad) renders
+_TC_BLOB = {}
+
+
+def _tc_blob(device):
+    key = str(device)
+    if key not in _TC_BLOB:
+        _TC_BLOB[key] = torch.empty(L.load().psl_tc_blob_floats(), dtype=torch.float32, device=device)
+    return _TC_BLOB[key]
+
+
 def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
                     affine, need_grad):
     lib = L.load()
@@ -185,6 +197,19 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
+    if USE_TENSOR_CORES and not need_grad and st.stage == 'color' and st.weighting == 'distance':
+        # geometry branch (fp32 FFMA kernel, writes occupancy + has_nb) then the colour branch on tcgen05
+        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, cfg.rgb_mode, cfg.weighting, cfg.min_nn, cfg.r2_group,
+                           cfg.is_tracker, 0, cfg.r2_scalar)
+        L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                   L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
+                                   L.ptr(has_nb), None, L.stream()), 'psl_decode_fwd[geometry]')
+        blob = _tc_blob(dev)
+        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.stream()),
+                'psl_color_fwd_tc')
+        return raw, has_nb, None, pstruct
     save = None
     if need_grad:
         per = lib.psl_decode_save_floats_per_sample(C.byref(cfg))

@@ -1,0 +1,68 @@
+"""tcgen05 building blocks (psl_tc.cuh): 3xTF32 GEMM with fp32 TMEM accumulation must match fp32/fp64 matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('K,N', [(8, 16), (40, 128), (56, 128), (128, 32), (160, 128)])
+def test_tc_gemm_3xtf32(mode, K, N):
+    from point_slam_b200 import _lib as L
+    lib = L.load()
+    if mode == 1 and K > 64:
+        pytest.skip('SS-form test operand does not fit in shared memory')
+    g = torch.Generator().manual_seed(K * 1000 + N + mode)
+    A = (torch.randn(128, K, generator=g) * 3).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    D = torch.zeros(128, N, device='cuda')
+    scratch = torch.empty(2 * N * K, device='cuda')
+    L.check(lib.psl_tc_gemm_test(L.ptr(A), L.ptr(W), L.ptr(D), L.ptr(scratch), K, N, mode, L.stream()), 'psl_tc_gemm_test')
+    torch.cuda.synchronize()
+    ref = (A.double() @ W.double().t())
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    err32 = float(((A @ W.t()).double() - ref).abs().max() / ref.abs().max())
+    print(f'mode {mode} K {K} N {N}: 3xTF32 err {err:.2e}  (fp32 matmul err {err32:.2e})')
+    assert err < 2e-6
+
+
+@pytest.mark.parametrize('name', ['mapper_color', 'tum_near_pcl', 'exposure_tracker', 's32_color', 'fixed_radius_zero_depth'])
+def test_color_branch_on_tensor_cores_matches_oracle(name):
+    """Inference render with the tcgen05 colour branch (3xTF32, TMEM-resident activations) vs the fp64 oracle and vs
+    the fp32 FFMA kernel, on the golden cases (all colour configurations: rel-pos on/off, exposure affine, S = 32)."""
+    import numpy as np
+    from point_slam_b200 import ops
+    from tests import cases as C
+    from tests.gpu_harness import build_objects, DEV
+    c = C.load_case(name)
+    o64 = C.run_oracle(c, torch.float64)
+    o32 = C.run_oracle(c, torch.float32)
+    cfg, decoders, npc, renderer = build_objects(c)
+    t = lambda k, dt=torch.float32: torch.from_numpy(np.asarray(c[k])).to(device=DEV, dtype=dt)
+    rg, rc = t('rand_geo'), t('rand_col')
+    decoders.draw_no_neighbor_vectors = lambda stage, device: (rg, rc if stage == 'color' else None)
+    if 'cam_tensor' in c:
+        from point_slam_b200.src import common
+        c2w = common.get_camera_from_tensor(t('cam_tensor'))
+        rays_o, rays_d = common.get_rays_from_uv(t('pix_i'), t('pix_j'), c2w, C.INTR['fx'], C.INTR['fy'], C.INTR['cx'], C.INTR['cy'], DEV)
+    else:
+        rays_o, rays_d = t('rays_o'), t('rays_d')
+    dyn = t('dynamic_r_query', torch.float64) if 'dynamic_r_query' in c else None
+    ef = t('exposure_feat') if 'exposure_feat' in c else None
+    outs = {}
+    for use_tc in (True, False):
+        ops.USE_TENSOR_CORES = use_tc
+        with torch.no_grad():
+            outs[use_tc] = renderer.render_batch_ray(npc, decoders, rays_d, rays_o, DEV, c['stage'], gt_depth=t('gt_depth'),
+                                                     npc_geo_feats=npc.get_geo_feats(), npc_col_feats=npc.get_col_feats(),
+                                                     is_tracker=c['is_tracker'], cloud_pos=npc.cloud_pos_tensor(),
+                                                     dynamic_r_query=dyn, exposure_feat=ef)
+    ops.USE_TENSOR_CORES = True
+    d_tc, v_tc, c_tc, m_tc = outs[True]
+    d_ff, v_ff, c_ff, m_ff = outs[False]
+    assert torch.equal(m_tc, m_ff) and torch.equal(d_tc, d_ff)                 # geometry branch is the same kernel
+    e_tc = C.rel_err(c_tc.cpu(), o64['color'])
+    e_ff = C.rel_err(c_ff.cpu(), o64['color'])
+    e_32 = C.rel_err(o32['color'], o64['color'])
+    print(f'{name}: colour rel err vs fp64  tcgen05 {e_tc:.2e}  ffma {e_ff:.2e}  fp32 oracle {e_32:.2e}')
+    assert e_tc <= max(1e-4, 3 * e_32)
