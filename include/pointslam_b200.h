@@ -65,6 +65,8 @@ typedef struct psl_grid {
     uint32_t capacity;            /* power of two                                                     */
     int32_t n;                    /* number of points                                                 */
     float cell;                   /* cell edge length in metres                                       */
+    float r_small;                /* first-pass search radius (0 = off): exact early exit when 8 points lie
+                                     inside it, else the query radius is searched (see k_knn)            */
 } psl_grid;
 
 size_t psl_grid_sort_ws_bytes(int64_t n);

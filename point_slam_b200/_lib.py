@@ -25,7 +25,7 @@ _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, 
 
 class Grid(C.Structure):                                   # psl_grid
     _fields_ = [('sorted_pts', _vp), ('table_keys', _vp), ('table_vals', _vp), ('capacity', C.c_uint32),
-                ('n', _i32), ('cell', _f32)]
+                ('n', _i32), ('cell', _f32), ('r_small', _f32)]
 
 
 N_PARAMS = 1 + 5 * 4 + 2 + 6 + 5 * 4 + 2                   # 51 pointers in psl_decoder_params

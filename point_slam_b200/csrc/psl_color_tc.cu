@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                         const int c0 = 64 * h + 32 * c;
                         tc::tmem_ld32(lb + TP + c0, xv);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100(xv[j] + b1[c0 + j]), xv[j], lo[j]);
+                        for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(xv[j] + b1[c0 + j]), xv[j], lo[j]);
                         tc::tmem_st32(lb + TP + c0, xv);
                         tc::tmem_st32(lb + TQ + c0, lo);
                     }
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     float v[32], lo[32];
                     tc::tmem_ld32(lb + dcol + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100(v[j] + bias[c0 + j]), v[j], lo[j]);
+                    for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(v[j] + bias[c0 + j]), v[j], lo[j]);
                     tc::tmem_st32(lb + dcol + c0, v);
                     tc::tmem_st32(lb + TR + c0, lo);
                 }

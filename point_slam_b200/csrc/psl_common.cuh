@@ -80,6 +80,14 @@ __device__ __forceinline__ float softplus100_grad(float x) {     // d/dx: z/(z+1
     const float z = expf(bx);
     return z / (z + 1.0f);
 }
+// Softplus(beta=100) with hardware ex2/lg2 approximations: |abs error| <~ 2e-9 (the output is >= 6.9e-3 wherever it
+// matters), used by the tensor-core epilogues where the transcendental, not the MMA, is the critical path.
+__device__ __forceinline__ float softplus100_fast(float x) {
+    const float bx = x * 100.0f;
+    const float e = __expf(fminf(bx, 20.0f));
+    const float y = __logf(1.0f + e) * 0.01f;
+    return bx > 20.0f ? x : y;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace psl

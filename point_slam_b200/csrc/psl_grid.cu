@@ -79,6 +79,7 @@ struct GridDev {
     uint32_t mask;
     int n;
     float inv_cell;
+    float r_small;      // radius of the first search pass (0 = single pass with the full query radius)
 };
 
 __device__ __forceinline__ uint2 grid_lookup(const GridDev& g, uint64_t key) {
@@ -179,9 +180,21 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
             tlt = thr_lt_of(r2);
             rf = sqrtf(fmaxf(tlt, 0.f)) * 1.001f + 1e-5f;
         }
+        // Two-pass search.  Pass 0 looks only inside r_small (a few times the typical 8th-neighbour distance): if a
+        // sample finds 8 points with D <= r_small^2 these ARE its 8 nearest (every point inside that ball was seen), so
+        // the result is exact; samples that do not fill their list force pass 1 with the full query radius.
+        float tins = tle, rcur = rf;               // insertion threshold / search radius of the current pass
+        bool small_pass = false;
+        if (g.r_small > 0.f) {
+            const float ts = g.r_small * g.r_small;
+            if (valid && ts < tle) { tins = ts; rcur = g.r_small * 1.001f + 1e-5f; }
+            small_pass = __any_sync(0xffffffffu, valid && ts < tle);
+        }
+      for (int pass = small_pass ? 0 : 1; pass < 2; ++pass) {
+        if (pass == 1) { tins = tle; rcur = rf; }
         // ---- warp AABB (already dilated by the radii) and its cell range --------------------------
-        float bx0 = valid ? qx - rf : FLT_MAX, by0 = valid ? qy - rf : FLT_MAX, bz0 = valid ? qz - rf : FLT_MAX;
-        float bx1 = valid ? qx + rf : -FLT_MAX, by1 = valid ? qy + rf : -FLT_MAX, bz1 = valid ? qz + rf : -FLT_MAX;
+        float bx0 = valid ? qx - rcur : FLT_MAX, by0 = valid ? qy - rcur : FLT_MAX, bz0 = valid ? qz - rcur : FLT_MAX;
+        float bx1 = valid ? qx + rcur : -FLT_MAX, by1 = valid ? qy + rcur : -FLT_MAX, bz1 = valid ? qz + rcur : -FLT_MAX;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
             for (int s = 0; s < cnt; ++s) {
                 const float sx = __shfl_sync(0xffffffffu, qx, s), sy = __shfl_sync(0xffffffffu, qy, s),
                             sz = __shfl_sync(0xffffffffu, qz, s);
-                const float sle = __shfl_sync(0xffffffffu, tle, s);
+                const float sle = __shfl_sync(0xffffffffu, tins, s);
                 unsigned long long keys[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) keys[k] = KEY_INF;
@@ -286,6 +299,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
             if (nstaged > 0) flush();
         }
         __syncwarp();
+        if (pass == 0) {
+            const bool done = !valid || tins >= tle || s_best[lane * 8 + 7] != KEY_INF;
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+      }
+        __syncwarp();
         // ---- write results: 4 queries x 8 slots per pass (128 B coalesced) -------------------------
         for (int sb = 0; sb < cnt; sb += 4) {
             const int s = sb + (lane >> 3), k = lane & 7;
@@ -316,6 +335,7 @@ static int make_grid_dev(const psl_grid* gh, GridDev* g) {
     g->mask = gh->capacity ? gh->capacity - 1 : 0;
     g->n = gh->n;
     g->inv_cell = 1.0f / gh->cell;
+    g->r_small = gh->r_small;
     return 0;
 }
 

@@ -77,12 +77,13 @@ class SpatialHash:
     """GPU-resident hash grid over the neural point cloud (K0).  Rebuilt on every append (about 1 ms for 2 M points);
     point indices are stable (the grid stores a sorted copy carrying the original index)."""
 
-    def __init__(self, cell: float = 0.08):
+    def __init__(self, cell: float = 0.08, two_pass: bool = True):
         self.cell = float(cell)
+        self.two_pass = two_pass
         self.n = 0
         self.sorted_pts = self.table_keys = self.table_vals = None
         self.capacity = 0
-        self.struct = L.Grid(None, None, None, 0, 0, self.cell)
+        self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0)
 
     def build(self, cloud_pos: torch.Tensor):
         lib = L.load()
@@ -91,7 +92,7 @@ class SpatialHash:
         dev = pos.device
         self.n = n
         if n == 0:
-            self.struct = L.Grid(None, None, None, 0, 0, self.cell)
+            self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0)
             return self
         ws_bytes = lib.psl_grid_sort_ws_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -107,8 +108,14 @@ class SpatialHash:
         L.check(lib.psl_grid_hash(L.ptr(keys), n, L.ptr(self.table_keys), L.ptr(self.table_vals), cap, L.stream()),
                 'psl_grid_hash')
         self.n_cells = n_cells.value
+        # first-pass radius: expect ~32 points inside it, estimated from the mean occupancy of the occupied cells
+        # (a cell of edge h cuts ~1.5 h^2 of surface); clamped to [h/4, h]
+        self.r_small = 0.0
+        if self.two_pass:
+            rs = math.sqrt(32.0 * 1.5 * self.cell ** 2 * max(self.n_cells, 1) / (math.pi * n))
+            self.r_small = float(min(max(rs, self.cell / 4), self.cell))
         self.struct = L.Grid(self.sorted_pts.data_ptr(), self.table_keys.data_ptr(), self.table_vals.data_ptr(),
-                             cap, n, self.cell)
+                             cap, n, self.cell, self.r_small)
         return self
 
 
@@ -170,6 +177,7 @@ class RenderSettings:
         self.radius_query, self.coef = float(radius_query), float(coef)
         self.encode_rel_pos, self.rgb_mode = bool(encode_rel_pos), int(rgb_mode)
         self.weighting, self.min_nn, self.is_tracker = weighting, int(min_nn), bool(is_tracker)
+        self.grad_mode = True
 
     def cfg(self, r2_group, r2_scalar):
         return L.DecodeCfg(L.STAGE[self.stage], int(self.encode_rel_pos), self.rgb_mode, L.WEIGHTING[self.weighting],
@@ -199,7 +207,7 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
     if USE_TENSOR_CORES and not need_grad and st.stage == 'color' and st.weighting == 'distance':
         # geometry branch (fp32 FFMA kernel, writes occupancy + has_nb) then the colour branch on tcgen05
-        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, cfg.rgb_mode, cfg.weighting, cfg.min_nn, cfg.r2_group,
+        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 0, cfg.r2_scalar)
         L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                    L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
@@ -289,7 +297,7 @@ class _RenderFn(torch.autograd.Function):
                                      L.ptr(r2_ray), r2s, L.ptr(z_vals), L.ptr(pos), L.ptr(I), L.ptr(D), L.ptr(nn),
                                      L.stream()), 'psl_raymarch_knn')
         cfg = st.cfg(S, r2s)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
         raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
                                                rand_col, aff, need_grad)
         depth = torch.empty((R,), dtype=torch.float32, device=dev)
@@ -348,7 +356,7 @@ class _DecodeFn(torch.autograd.Function):
         D, I, nn = knn_query_r2(grid, pos, r2_pts, st.radius_query, r2_group)
         r2s = float(np.float32(st.radius_query ** 2))
         cfg = st.cfg(r2_group, r2s)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
         raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_pts, cloud, geo, col, rand_geo,
                                                rand_col, aff, need_grad)
         ctx.st, ctx.cfg = st, cfg
@@ -426,6 +434,7 @@ def render(st: RenderSettings, grid: SpatialHash, params: Sequence[torch.Tensor]
         rand_geo = torch.zeros(32, device=dev)
     if rand_col is None:
         rand_col = torch.zeros(32, device=dev)
+    st.grad_mode = torch.is_grad_enabled()
     return _RenderFn.apply(st, grid, _f32c(gt_depth).reshape(-1), z_override, r2_ray, _f32c(rand_geo), _f32c(rand_col),
                            cloud_pos, rays_o, rays_d, geo_feats, col_feats, affine, *params)
 
@@ -437,6 +446,7 @@ def decode(st: RenderSettings, grid: SpatialHash, params, p, cloud_pos, geo_feat
         rand_geo = torch.zeros(32, device=dev)
     if rand_col is None:
         rand_col = torch.zeros(32, device=dev)
+    st.grad_mode = torch.is_grad_enabled()
     return _DecodeFn.apply(st, grid, r2_pts, int(r2_group), _f32c(rand_geo), _f32c(rand_col), cloud_pos, p, geo_feats,
                            col_feats, affine, *params)
 

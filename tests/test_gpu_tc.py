@@ -61,6 +61,8 @@ def test_color_branch_on_tensor_cores_matches_oracle(name):
     d_tc, v_tc, c_tc, m_tc = outs[True]
     d_ff, v_ff, c_ff, m_ff = outs[False]
     assert torch.equal(m_tc, m_ff) and torch.equal(d_tc, d_ff)                 # geometry branch is the same kernel
+    assert not torch.equal(c_tc, c_ff), 'tensor-core path was not taken'
+    assert C.rel_err(c_tc.cpu(), c_ff.cpu()) < 2e-5
     e_tc = C.rel_err(c_tc.cpu(), o64['color'])
     e_ff = C.rel_err(c_ff.cpu(), o64['color'])
     e_32 = C.rel_err(o32['color'], o64['color'])
