@@ -140,6 +140,10 @@ class GpuScene:
         self.resident = [self._to_device(f) for f in self.frames_host[N_KEYFRAMES:]]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
         self.out_host = torch.empty(8, dtype=torch.float32).pin_memory()
+        from point_slam_b200 import graphed as G
+        self.G = G
+        self.tracker = G.GraphedTracker(self.renderer, self.npc, self.decoders, INTR, TRACK_PIX, device, edge=(100, 100))
+        self.mapper = G.GraphedMapper(self.renderer, self.npc, self.decoders, INTR, MAP_PIX, device)
 
     def _to_device(self, f):
         d = self.device
@@ -147,55 +151,61 @@ class GpuScene:
                     dyn_r_query=torch.from_numpy(f['dyn_r_query']).to(d),
                     c2w=torch.from_numpy(f['c2w'][:3, :4].astype(np.float32)).to(d))
 
-    def step(self, k, from_host):
-        """Process frame k.  Returns the number of ray-samples rendered (fwd+bwd)."""
+    def step(self, k, from_host, graphs=True):
+        """Process frame k: 40 tracking + 60 mapping iterations.  graphs=True: each iteration is one CUDA-graph replay of the
+        static-shape shell (point_slam_b200/graphed.py); graphs=False: the same static-shape iterations launched eagerly
+        (used for the per-kernel timing pass).  Returns the number of ray-samples rendered (fwd+bwd)."""
         d = self.device
         fh = self.frames_host[N_KEYFRAMES + k]
-        if from_host:
-            cur = {n: t.to(d, non_blocking=True) for n, t in self.pinned[k].items()}
-            cur['c2w'] = torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d)
+        src = self.pinned[k] if from_host else self.resident[k]
+        cam0 = cam_tensor_from_c2w(fh['c2w'], 0.01, self.rng).to(d, non_blocking=True)
+        tr = self.tracker
+        tr.load_frame(src['color'], src['depth'], src['dyn_r_query'], cam0)        # H2D from pinned memory in the e2e pass
+        npc, dec = self.npc, self.decoders
+        if graphs:
+            loss = tr.run(TRACK_ITERS)
         else:
-            cur = self.resident[k]
-        npc, dec, render = self.npc, self.decoders, self.renderer.render_batch_ray
-        cloud = npc.cloud_pos_tensor()
-        samples = 0
-        # ---- tracking: Adam on [quat, T] (Tracker.py:283-332, separate_LR off for brevity) -------------------------
-        cam = cam_tensor_from_c2w(fh['c2w'], 0.01, self.rng).to(d).requires_grad_(True)
-        opt = torch.optim.Adam([cam], lr=0.002)
-        geo, col = npc.get_geo_feats(), npc.get_col_feats()
-        loss = None
-        for _ in range(TRACK_ITERS):
-            loss, n = IT.tracker_iteration(render, npc, dec, cam, opt, cur['color'], cur['depth'], cur['dyn_r_query'], INTR,
-                                           TRACK_PIX, d, geo, col, cloud, edge=(100, 100))
-            samples += n * S
-        # ---- mapping: features in the current frustum + colour decoder ------------------------------------------------
-        idx = IT.frustum_indices(cloud, cur['c2w'], INTR)
-        state = IT.MapperState(npc, dec, idx)
-        kfs = [cur] + self.keyframes
-        for it in range(MAP_ITERS):
-            loss, n = IT.mapper_iteration(render, npc, dec, state, kfs, INTR, MAP_PIX, d,
-                                          'geometry' if it < GEO_ITERS else 'color', cloud)
-            samples += n * S
+            flags = [(p, p.requires_grad) for p in dec.parameters()]
+            for p, _ in flags:
+                p.requires_grad_(False)
+            for _ in range(TRACK_ITERS):
+                tr._iter()
+            for p, f in flags:
+                p.requires_grad_(f)
+            loss = tr.loss
+        cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn,
+                   c2w=torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True))
+        idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], INTR)
+        state = IT.MapperState(npc, dec, idx, capturable=True)
+        self.mapper.begin_frame(state, [cur] + self.keyframes)
+        if graphs:
+            self.mapper.run('geometry', GEO_ITERS)
+            loss = self.mapper.run('color', MAP_ITERS - GEO_ITERS)
+        else:
+            for it in range(MAP_ITERS):
+                self.mapper._iter('geometry' if it < GEO_ITERS else 'color')
+            loss = self.mapper.loss
         if from_host:
-            self.out_host[:7].copy_(cam.detach(), non_blocking=True)
+            self.out_host[:7].copy_(tr.cam.detach(), non_blocking=True)
             self.out_host[7:8].copy_(loss.reshape(1), non_blocking=True)
-        return samples
+        return (TRACK_ITERS * TRACK_PIX + MAP_ITERS * (MAP_PIX // (1 + N_KEYFRAMES)) * (1 + N_KEYFRAMES)) * S
 
 
 def timed_steps(scene, steps, first, from_host, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
     samples = 0
     for k in range(steps):
         samples += scene.step(first + k, from_host)
-    e1.record()
+        ev[k + 1].record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    return e0.elapsed_time(e1), samples
+    per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), samples, per_step
 
 
 def run_ours(args):
@@ -215,16 +225,17 @@ def run_ours(args):
     for k in range(args.warmup):
         scene.step(k, False)
     clocks = Clocks(local) if rank == 0 else None
-    l0 = lib.psl_launch_count()
-    ms, samples = timed_steps(scene, args.steps, args.warmup, False, dist)
-    launches = lib.psl_launch_count() - l0
-    ms_e2e, samples_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
+    ms, samples, per_step = timed_steps(scene, args.steps, args.warmup, False, dist)
+    ms_e2e, samples_e2e, per_step_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
     clk = clocks.stop() if clocks else None
     # per-kernel device time of one more step (CUDA events on the launching stream inside the library)
+    # (the same static-shape iterations launched eagerly: graph replays bypass the host-side event hooks)
+    l0 = lib.psl_launch_count()
     _lib.timing_enable(True)
-    n_prof = scene.step(args.warmup, False)
+    n_prof = scene.step(args.warmup, False, graphs=False)
     prof = _lib.timing_collect()
     _lib.timing_enable(False)
+    launches = (lib.psl_launch_count() - l0) * args.steps           # kernels of this library per step x timed steps
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,7 +273,7 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'C2 Replica-office0-like frame: 40 track it x 1500 rays + 60 map it x 5000 rays, S=5, '
                                f'{args.points} pts, 640x480; one scene per GPU', 'points': args.points,
-                   'work_per_step': 'fwd + loss + bwd + Adam (tracker pose; mapper features + colour decoder)',
+                   'work_per_step': 'fwd + loss + bwd + Adam (tracker pose; mapper features + colour decoder); every iteration is one CUDA-graph replay of a static-shape shell',
                    'l2': 'inputs larger than L2 (cloud+features 134 MB, saved activations ~290 MB / mapper iteration)',
                    'parallelism': f'scene-per-gpu x{world}'},
         'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes, 'd2h_bytes_per_step': 32,
@@ -275,6 +286,7 @@ def run_ours(args):
                      'avg_launch_ms': top_ms / max(top_n, 1),
                      'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
                      'fp32_tflops_fwd_bwd': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12},
+        'step_ms': [round(x, 1) for x in per_step], 'step_ms_e2e': [round(x, 1) for x in per_step_e2e],
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
     }

@@ -54,14 +54,15 @@ def frustum_indices(cloud_pos, c2w, intr, margin=4):
 class MapperState:
     """Optimisable slices + Adam, set up like Mapper.optimize_map (src/Mapper.py:345-402)."""
 
-    def __init__(self, npc, decoders, indices, lr_dec=0.005, lr_geo=0.005, lr_col=0.005):
+    def __init__(self, npc, decoders, indices, lr_dec=0.005, lr_geo=0.005, lr_col=0.005, capturable=False):
         self.indices = indices
         self.npc_geo = npc.get_geo_feats().detach().clone()
         self.npc_col = npc.get_col_feats().detach().clone()
         self.geo = self.npc_geo[indices].detach().clone().requires_grad_(True)
         self.col = self.npc_col[indices].detach().clone().requires_grad_(True)
         self.optimizer = torch.optim.Adam([{'params': list(decoders.color_decoder.parameters()), 'lr': lr_dec},
-                                           {'params': [self.geo], 'lr': lr_geo}, {'params': [self.col], 'lr': lr_col}])
+                                           {'params': [self.geo], 'lr': lr_geo}, {'params': [self.col], 'lr': lr_col}],
+                                          capturable=capturable)
 
 
 def mapper_iteration(render, npc, decoders, state, keyframes, intr, n_pixels, device, stage, cloud_pos, w_color=0.1):

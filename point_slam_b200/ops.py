@@ -243,8 +243,14 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
     d_colpair = None
     if want_col:
         d_colpair = torch.empty((M, 8, 32) if rel else (M, 32), dtype=torch.float32, device=dev)
-    grads = [torch.zeros_like(p) if (n and (color or name.startswith('g_'))) else None
-             for p, n, name in zip(params, needs, L_PARAM_NAMES)]
+    # one flat buffer for all requested parameter gradients (k_reduce_partials writes every element: no memset needed)
+    want = [bool(n and (color or name.startswith('g_')) and name != 'c_B') for n, name in zip(needs, L_PARAM_NAMES)]
+    sizes = [p.numel() if w else 0 for p, w in zip(params, want)]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev) if any(want) else None
+    grads, off = [], 0
+    for p, w, n_el in zip(params, want, sizes):
+        grads.append(flat[off:off + n_el].view(p.shape) if w else None)
+        off += n_el
     gstruct = _param_struct(grads)
     pstruct = _param_struct(params)
     d_aff = torch.zeros(12, dtype=torch.float32, device=dev) if want_affine else None

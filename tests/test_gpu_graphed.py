@@ -1,0 +1,74 @@
+"""Static-shape / CUDA-graph iteration shells (point_slam_b200/graphed.py) against the reference-style shells."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _setup():
+    import bench
+    scene = bench.GpuScene(0, DEV, 200000, 1)
+    return bench, scene
+
+
+def test_static_tracker_iteration_matches_reference_style_shell():
+    from point_slam_b200 import iteration as IT, graphed as G
+    bench, scene = _setup()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.01, scene.rng).to(DEV)
+    out = {}
+    for kind in ('ref', 'static'):
+        cam = cam0.clone().requires_grad_(True)
+        opt = torch.optim.SGD([cam], lr=0.0)                 # keep the pose fixed: compare loss and gradient only
+        torch.manual_seed(5)
+        if kind == 'ref':
+            loss, _ = IT.tracker_iteration(ren.render_batch_ray, npc, dec, cam, opt, cur['color'], cur['depth'], cur['dyn_r_query'],
+                                           bench.INTR, 1500, DEV, npc.get_geo_feats(), npc.get_col_feats(), npc.cloud_pos_tensor(),
+                                           edge=(100, 100))
+            out[kind] = (float(loss), None)
+        else:
+            loss = G.tracker_iteration_static(ren, npc, dec, cam, cur['color'], cur['depth'], cur['dyn_r_query'], bench.INTR, 1500,
+                                              DEV, npc.get_geo_feats(), npc.get_col_feats(), npc.cloud_pos_tensor(), (100, 100))
+            out[kind] = (float(loss), cam.grad.clone())
+    # the reference-style shell zeroes the gradient after its optimizer step; recompute it for the comparison
+    cam = cam0.clone().requires_grad_(True)
+    torch.manual_seed(5)
+
+    class Keep(torch.optim.SGD):
+        def zero_grad(self, *a, **k):
+            pass
+    IT.tracker_iteration(ren.render_batch_ray, npc, dec, cam, Keep([cam], lr=0.0), cur['color'], cur['depth'], cur['dyn_r_query'],
+                         bench.INTR, 1500, DEV, npc.get_geo_feats(), npc.get_col_feats(), npc.cloud_pos_tensor(), edge=(100, 100))
+    g_ref = cam.grad
+    assert abs(out['ref'][0] - out['static'][0]) / abs(out['ref'][0]) < 1e-5
+    assert float((g_ref - out['static'][1]).abs().max() / g_ref.abs().max()) < 1e-4
+
+
+def test_graphed_tracker_and_mapper_run_and_optimise():
+    from point_slam_b200 import iteration as IT, graphed as G
+    bench, scene = _setup()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    gt = G.GraphedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.02, scene.rng).to(DEV)
+    gt.load_frame(cur['color'], cur['depth'], cur['dyn_r_query'], cam0)
+    l0 = float(gt.run(1))
+    l1 = float(gt.run(40))
+    torch.cuda.synchronize()
+    assert np.isfinite(l0) and np.isfinite(l1) and l1 < l0, (l0, l1)
+    assert float((gt.cam.detach() - cam0).abs().max()) > 0
+    # mapper
+    gm = G.GraphedMapper(ren, npc, dec, bench.INTR, 5000, DEV)
+    idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
+    state = IT.MapperState(npc, dec, idx, capturable=True)
+    gm.begin_frame(state, [cur] + scene.keyframes)
+    g0 = state.geo.detach().clone()
+    la = float(gm.run('geometry', 3))
+    lb = float(gm.run('geometry', 20))
+    lc = float(gm.run('color', 10))
+    torch.cuda.synchronize()
+    assert np.isfinite(la) and np.isfinite(lb) and np.isfinite(lc) and lb < la
+    assert float((state.geo.detach() - g0).abs().max()) > 0
