@@ -176,8 +176,7 @@ class GpuScene:
         cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn,
                    c2w=torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True))
         idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], INTR)
-        state = IT.MapperState(npc, dec, idx, capturable=True)
-        self.mapper.begin_frame(state, [cur] + self.keyframes)
+        self.mapper.begin_frame(idx, [cur] + self.keyframes)
         if graphs:
             self.mapper.run('geometry', GEO_ITERS)
             loss = self.mapper.run('color', MAP_ITERS - GEO_ITERS)

@@ -179,17 +179,69 @@ class GraphedTracker:
         return self.loss
 
 
-class GraphedMapper:
-    """The joint loop of Mapper.optimize_map for one frame: one graph per stage, re-captured per frame because the
-    frustum-selected feature slices change size."""
+class _MapState:
+    pass
 
-    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, w_color=0.1):
+
+class GraphedMapper:
+    """The joint loop of Mapper.optimize_map as replays of ONE captured graph per stage for the whole run.
+
+    The frustum-selected feature slices change size from frame to frame; to keep every shape static the index list is
+    padded to a fixed capacity `u_max` with the index of a dummy extra feature row (row N of (N+1)-row copies of the feature
+    tensors): padded slots scatter into / gather from that row, which no kNN index ever references, so they receive zero
+    gradient and Adam leaves them at zero.  Graphs are re-captured only when the cloud size, the capacity or the spatial
+    hash changes (e.g. after add_neural_points)."""
+
+    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, w_color=0.1, lr_dec=0.005, lr_geo=0.005, lr_col=0.005,
+                 u_max=1 << 17):
         self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.w = renderer, npc, decoders, intr, n_pixels, device, w_color
+        self.lrs = (lr_dec, lr_geo, lr_col)
         self.loss = torch.zeros((), device=device)
+        self.u_max = int(u_max)
         self.graphs = {}
         self.state = None
+        self.key = None
         self.warm = False
-        self.pool = torch.cuda.graph_pool_handle()     # one memory pool for the per-frame graphs (no cudaMalloc per frame)
+
+    def _alloc(self, N, n_kf):
+        H, W = self.intr['H'], self.intr['W']
+        d = self.dev
+        st = _MapState()
+        st.indices = torch.full((self.u_max,), N, dtype=torch.int64, device=d)
+        st.npc_geo = torch.zeros(N + 1, 32, device=d)
+        st.npc_col = torch.zeros(N + 1, 32, device=d)
+        st.geo = torch.zeros(self.u_max, 32, device=d, requires_grad=True)
+        st.col = torch.zeros(self.u_max, 32, device=d, requires_grad=True)
+        st.optimizer = torch.optim.Adam([{'params': list(self.dec.color_decoder.parameters()), 'lr': self.lrs[0]},
+                                         {'params': [st.geo], 'lr': self.lrs[1]}, {'params': [st.col], 'lr': self.lrs[2]}],
+                                        capturable=True)
+        self.state = st
+        self.keyframes = dict(color=torch.zeros(n_kf, H, W, 3, device=d), depth=torch.zeros(n_kf, H, W, device=d),
+                              c2w=torch.zeros(n_kf, 3, 4, device=d), dyn_r_query=torch.zeros(n_kf, H, W, dtype=torch.float64, device=d))
+        self.graphs = {}
+
+    def begin_frame(self, indices, keyframes):
+        """indices: (U,) int64 rows of the feature tensors to optimise; keyframes: list of dicts (color, depth, c2w, dyn_r_query)."""
+        N, U = self.npc.pts_num(), int(indices.shape[0])
+        while U > self.u_max:
+            self.u_max *= 2
+        key = (N, self.u_max, len(keyframes), self.npc.spatial_hash().sorted_pts.data_ptr())
+        if key != self.key:
+            self._alloc(N, len(keyframes))
+            self.key = key
+        st = self.state
+        self.n_used = U
+        with torch.no_grad():
+            st.indices.fill_(N)
+            st.indices[:U] = indices
+            st.npc_geo[:N] = self.npc.get_geo_feats()
+            st.npc_col[:N] = self.npc.get_col_feats()
+            st.geo.copy_(st.npc_geo[st.indices])
+            st.col.copy_(st.npc_col[st.indices])
+            for i, kf in enumerate(keyframes):
+                self.keyframes['color'][i].copy_(kf['color']); self.keyframes['depth'][i].copy_(kf['depth'])
+                self.keyframes['c2w'][i].copy_(kf['c2w'][:3, :4]); self.keyframes['dyn_r_query'][i].copy_(kf['dyn_r_query'])
+        _reset_adam(st.optimizer)
 
     def _iter(self, stage):
         st = self.state
@@ -199,11 +251,6 @@ class GraphedMapper:
         st.optimizer.step()
         st.npc_geo, st.npc_col = st.npc_geo.detach(), st.npc_col.detach()
         self.loss.copy_(loss)
-
-    def begin_frame(self, state, keyframes):
-        """state: iteration.MapperState built with capturable Adam; keyframes: list of dicts with static tensors."""
-        self.graphs.clear()                            # releases the previous frame's graphs back into the shared pool
-        self.state, self.keyframes = state, stack_keyframes(keyframes)
 
     def run(self, stage, n_iters):
         done = 0
@@ -217,9 +264,15 @@ class GraphedMapper:
                 self.warm = True
                 done = 1
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.pool):      # capture records the iteration, it does not execute it
+            with torch.cuda.graph(g):                      # capture records the iteration, it does not execute it
                 self._iter(stage)
             self.graphs[stage] = g
         for _ in range(n_iters - done):
             self.graphs[stage].replay()
         return self.loss
+
+    def write_back(self):
+        """Optimised slices -> the neural point cloud (Mapper.py:605-610)."""
+        st, U = self.state, self.n_used
+        self.npc.update_geo_feats(st.geo.detach()[:U], st.indices[:U])
+        self.npc.update_col_feats(st.col.detach()[:U], st.indices[:U])

@@ -63,8 +63,8 @@ def test_graphed_tracker_and_mapper_run_and_optimise():
     # mapper
     gm = G.GraphedMapper(ren, npc, dec, bench.INTR, 5000, DEV)
     idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
-    state = IT.MapperState(npc, dec, idx, capturable=True)
-    gm.begin_frame(state, [cur] + scene.keyframes)
+    gm.begin_frame(idx, [cur] + scene.keyframes)
+    state = gm.state
     g0 = state.geo.detach().clone()
     la = float(gm.run('geometry', 3))
     lb = float(gm.run('geometry', 20))
@@ -72,3 +72,11 @@ def test_graphed_tracker_and_mapper_run_and_optimise():
     torch.cuda.synchronize()
     assert np.isfinite(la) and np.isfinite(lb) and np.isfinite(lc) and lb < la
     assert float((state.geo.detach() - g0).abs().max()) > 0
+    assert float(state.geo.detach()[gm.n_used:].abs().max()) == 0.0          # padded slots never move
+    before = npc.get_geo_feats().clone()
+    gm.write_back()
+    assert not torch.equal(before, npc.get_geo_feats())
+    gm.begin_frame(idx[: idx.shape[0] // 2], [cur] + scene.keyframes)         # a different frustum: same graphs are reused
+    n_graphs = len(gm.graphs)
+    ld = float(gm.run('color', 5))
+    assert np.isfinite(ld) and len(gm.graphs) == n_graphs
