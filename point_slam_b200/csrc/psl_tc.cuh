@@ -39,6 +39,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// (MN-major tf32 operands without swizzle were tried for the weight-gradient GEMM and return zeros on sm_100a; the
+// wgrad kernel therefore transposes while staging and keeps every operand K-major.)
 
 // D[tmem] (+)= A[tmem] * B[smem]^T     (single thread issues)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

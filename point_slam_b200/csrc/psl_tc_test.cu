@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm_test(const float* __restrict
     if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
+
 }  // namespace psl
 
 using namespace psl;
-
 // A (128,K), W (N,K), D (128,N) device fp32; scratch: 2*N*K floats.  K multiple of 8 (<= 160), N multiple of 16 (<= 128).
 extern "C" int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode,
                                 psl_stream_t stream) {
