@@ -217,7 +217,7 @@ int psl_tc_pack_params(const psl_decoder_params* params_host, float* tc_blob, ps
 int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
                      const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos,
                      const float* col_feats, const float* rand_col, const float* exposure_affine, float* raw,
-                     psl_stream_t stream);
+                     float* save /* NULL, or the psl_decode_fwd save buffer (training) */, psl_stream_t stream);
 
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);

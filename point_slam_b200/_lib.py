@@ -77,7 +77,7 @@ _SIGS = {
     'psl_ray_mask': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     'psl_tc_blob_floats': (_sz, []),
     'psl_tc_pack_params': (C.c_int, [C.POINTER(DecoderParams), _vp, _vp]),
-    'psl_color_fwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_color_fwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)

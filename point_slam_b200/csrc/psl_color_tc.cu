@@ -57,6 +57,7 @@ struct Args {
     const int* I; const float* D; const int* nnum; const double* r2;
     const float* cloud_pos; const float* col_feats; const float* rand_col; const float* affine;
     float* raw;                         // (m,4): xyz written here, w (occupancy) untouched
+    float* save;                        // training forward: pre-activations etc. for the backward (psl_decode.cuh SaveLayout)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -148,6 +149,7 @@ __device__ __forceinline__ void worker_signal(uint64_t* a_ready) {
     tc::mbar_arrive(a_ready);
 }
 
+template <bool SAVE>
 __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sVec = reinterpret_cast<float*>(smem + SB_VEC);
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool rel = a.cfg.encode_rel_pos != 0;
+    const SaveLayout SL = save_layout(1, a.cfg.encode_rel_pos);
+    const long long M = a.m;
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
@@ -350,7 +354,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                         const int c0 = 64 * h + 32 * c;
                         tc::tmem_ld32(lb + TP + c0, xv);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(xv[j] + b1[c0 + j]), xv[j], lo[j]);
+                        for (int j = 0; j < 32; ++j) xv[j] += b1[c0 + j];
+                        if (SAVE && inb) {
+                            float4* dst = reinterpret_cast<float4*>(a.save + SL.nz1 * M + (m * 8 + k) * 128 + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) dst[q] = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(xv[j]), xv[j], lo[j]);
                         tc::tmem_st32(lb + TP + c0, xv);
                         tc::tmem_st32(lb + TQ + c0, lo);
                     }
@@ -360,7 +371,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     float f[16];
                     tc::tmem_ld16(lb + TSP + 16 * h, f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) cacc[j] = fmaf(wn[k], f[j] + b2[16 * h + j], cacc[j]);
+                    for (int j = 0; j < 16; ++j) f[j] += b2[16 * h + j];
+                    if (SAVE && inb) {
+                        float4* dst = reinterpret_cast<float4*>(a.save + SL.nf * M + (m * 8 + k) * 32 + 16 * h);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cacc[j] = fmaf(wn[k], f[j], cacc[j]);
                 }
             } else {
 #pragma unroll 1
@@ -377,7 +395,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
             {   // ---- c (hi/lo) -> TMEM region C ; colour embedding (hi/lo) -> shared memory A operand
                 float chi[16], clo[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) tc::split_tf32(has ? cacc[j] : sRand[16 * h + j], chi[j], clo[j]);
+                for (int j = 0; j < 16; ++j) cacc[j] = has ? cacc[j] : sRand[16 * h + j];
+                if (SAVE && inb) {
+                    float4* dst = reinterpret_cast<float4*>(a.save + SL.cc * M + m * 32 + 16 * h);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(cacc[4 * q], cacc[4 * q + 1], cacc[4 * q + 2], cacc[4 * q + 3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tc::split_tf32(cacc[j], chi[j], clo[j]);
                 tc::tmem_st16(lb + TCC + 16 * h, chi);
                 tc::tmem_st16(lb + TCC + 32 + 16 * h, clo);
                 const float x = __fmul_rn(kTwoPi, px), y = __fmul_rn(kTwoPi, py), z = __fmul_rn(kTwoPi, pz);
@@ -404,7 +429,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     float v[32], lo[32];
                     tc::tmem_ld32(lb + dcol + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(v[j] + bias[c0 + j]), v[j], lo[j]);
+                    for (int j = 0; j < 32; ++j) v[j] += bias[c0 + j];
+                    if (SAVE && inb) {
+                        float4* dst = reinterpret_cast<float4*>(a.save + SL.cz * M + ((long long)l * M + m) * 128 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(v[j]), v[j], lo[j]);
                     tc::tmem_st32(lb + dcol + c0, v);
                     tc::tmem_st32(lb + TR + c0, lo);
                 }
@@ -460,23 +492,25 @@ extern "C" int psl_tc_pack_params(const psl_decoder_params* P, float* blob, psl_
 extern "C" int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m,
                                 const int32_t* I, const float* D, const int32_t* nnum, const double* r2,
                                 const float* cloud_pos, const float* col_feats, const float* rand_col,
-                                const float* exposure_affine, float* raw, psl_stream_t stream) {
+                                const float* exposure_affine, float* raw, float* save, psl_stream_t stream) {
     PSL_REQUIRE(cfg && tc_blob && pos && I && D && nnum && col_feats && rand_col && raw, "NULL argument");
     PSL_REQUIRE(!cfg->encode_rel_pos || cloud_pos, "rel-pos encoding needs cloud_pos");
     PSL_REQUIRE(cfg->rgb_mode != PSL_RGB_AFFINE_SIGMOID || exposure_affine, "affine mode needs exposure_affine");
     if (m == 0) return 0;
     ctc::Args a{};
     a.cfg = *cfg; a.blob = tc_blob; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
-    a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw;
+    a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.save = save;
     const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
     static bool attr_set = false;
     if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
         attr_set = true;
     }
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     TimingScope ts(T_DECODE_FWD, as_stream(stream));
-    ctc::k_color_fwd_tc<<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
+    if (save) ctc::k_color_fwd_tc<true><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
+    else ctc::k_color_fwd_tc<false><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -62,7 +62,7 @@ __host__ __device__ inline SaveLayout save_layout(int stage_color, int rel) {
     L.gh = o; o += 5 * 32;
     L.cc = o; if (stage_color) o += 32;
     L.cz = o; if (stage_color) o += 5 * 128;
-    L.ch = o; if (stage_color) o += 5 * 128;
+    L.ch = o;                                  // (h is recomputed by the backward from z and c: not stored)
     L.nz1 = o; if (stage_color && rel) o += 8 * 128;
     L.nf = o; if (stage_color && rel) o += 8 * 32;
     L.total = o;
@@ -82,14 +82,14 @@ struct DecodeArgs {
 // one dense layer for the 8 samples of a warp: acc[j][s] += sum_k Wt[k][lane+32j] * in[k][s]
 template <int NJ>
 __device__ __forceinline__ void dense8(float (&acc)[NJ][8], const float* __restrict__ in, int K,
-                                       const float* __restrict__ Wt, int lane) {
+                                       const float* __restrict__ Wt, int lane, int ldw = 32 * NJ) {
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(in + k * LD);
         const float4 a1 = *reinterpret_cast<const float4*>(in + k * LD + 4);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const float w = Wt[k * (32 * NJ) + lane + 32 * j];
+            const float w = Wt[k * ldw + lane + 32 * j];
             acc[j][0] = fmaf(w, a0.x, acc[j][0]); acc[j][1] = fmaf(w, a0.y, acc[j][1]);
             acc[j][2] = fmaf(w, a0.z, acc[j][2]); acc[j][3] = fmaf(w, a0.w, acc[j][3]);
             acc[j][4] = fmaf(w, a1.x, acc[j][4]); acc[j][5] = fmaf(w, a1.y, acc[j][5]);

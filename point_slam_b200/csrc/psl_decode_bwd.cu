@@ -148,6 +148,34 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
     for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
+constexpr int FCT_LD = 132;                      // padded row stride of the transposed fc_c matrix in shared memory
+constexpr int U_FCT = (128 + 40) * LD;           // offsets inside the union buffer sU
+constexpr int U_BC = U_FCT + 32 * FCT_LD;
+static_assert(U_BC + 128 <= B_U_FLOATS, "fc_c staging does not fit");
+
+// stage Fc (128,32) transposed as [32][FCT_LD] and its bias (all threads of the CTA)
+__device__ __forceinline__ void stage_fct(float* sU, const float* __restrict__ Fc, const float* __restrict__ bc) {
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) sU[U_FCT + (e & 31) * FCT_LD + (e >> 5)] = __ldg(Fc + e);
+    for (int e = threadIdx.x; e < 128; e += blockDim.x) sU[U_BC + e] = __ldg(bc + e);
+}
+
+// h_i = softplus(z_i) + Fc_i c + bc_i for the 8 samples of this warp (the forward keeps only z): h[j][s], channel lane+32j
+__device__ __forceinline__ void recompute_h(float (&h)[4][8], const float* sU, const float* sC_cols, const float* __restrict__ zsave,
+                                            long long M, long long m0, int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) h[j][s] = sU[U_BC + lane + 32 * j];
+    dense8<4>(h, sC_cols, 32, sU + U_FCT, lane, FCT_LD);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const float z = (m0 + s < M) ? zsave[(m0 + s) * 128 + lane + 32 * j] : 0.f;
+            h[j][s] = (m0 + s < M) ? __fadd_rn(softplus100(z), h[j][s]) : 0.f;
+        }
+}
+
 __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long long n_tiles) {
     extern __shared__ __align__(16) float smem[];
     float* sDH = smem + B_DH;
@@ -218,14 +246,19 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
         if (color) {
             // ---- B1: output layer ------------------------------------------------------------------------------
             // h4 -> sU (as [128][LD]) for dWo; out = Wo h4 + bo (needed only for the affine mode)
+            // c (interpolated colour feature): needed to rebuild h_i = softplus(z_i) + Fc_i c + bc_i and for the fc_c gradients
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                sC[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.cc * M + (m0 + s) * 32 + lane] : 0.f;
+            __syncthreads();
+            stage_fct(sU, a.P.c_Wc[4], a.P.c_bc[4]);
+            __syncthreads();
             float h4[4][8];
+            recompute_h(h4, sU, sC + col0, f.save + SL.cz * M + 4ll * M * 128, M, m0, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    h4[j][s] = (m0 + s < M) ? f.save[SL.ch * M + (4ll * M + m0 + s) * 128 + lane + 32 * j] : 0.f;
-                    sU[(lane + 32 * j) * LD + col0 + s] = h4[j][s];
-                }
+                for (int s = 0; s < 8; ++s) sU[(lane + 32 * j) * LD + col0 + s] = h4[j][s];
             float wo[3][4];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -307,10 +340,6 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
             __syncthreads();
 
             // ---- B2: trunk layers 4..0 ----------------------------------------------------------------------------
-            // c (interpolated colour feature) for the fc_c gradients
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                sC[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.cc * M + (m0 + s) * 32 + lane] : 0.f;
             float dcc[1][8];
 #pragma unroll
             for (int s = 0; s < 8; ++s) dcc[0][s] = 0.f;
@@ -342,12 +371,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
                 float* sIn = sU;
                 float* sEmb = sU + 128 * LD;
                 if (i >= 1) {
+                    __syncthreads();                         // everyone is done with the fc_c stage of step (a)
+                    stage_fct(sU, a.P.c_Wc[i - 1], a.P.c_bc[i - 1]);
+                    __syncthreads();
+                    float hp[4][8];
+                    recompute_h(hp, sU, sC + col0, f.save + SL.cz * M + (long long)(i - 1) * M * 128, M, m0, lane);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int s = 0; s < 8; ++s)
-                            sIn[(lane + 32 * j) * LD + col0 + s] =
-                                (m0 + s < M) ? f.save[SL.ch * M + ((long long)(i - 1) * M + m0 + s) * 128 + lane + 32 * j] : 0.f;
+                        for (int s = 0; s < 8; ++s) sIn[(lane + 32 * j) * LD + col0 + s] = hp[j][s];
                 }
                 if ((i == 0 || i == 3) && lane < PSL_COL_EMB) {
                     const float b0 = __ldg(a.P.c_B + lane), b1 = __ldg(a.P.c_B + 20 + lane), b2 = __ldg(a.P.c_B + 40 + lane);

@@ -299,7 +299,6 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_fwd(DecodeArgs a, long
                         hout[(lane + 32 * j) * LD + s] = h[j][s];
                         if (SAVE && m0 + s < M) {
                             a.save[SL.cz * M + ((long long)i * M + m0 + s) * 128 + lane + 32 * j] = acc[j][s];
-                            a.save[SL.ch * M + ((long long)i * M + m0 + s) * 128 + lane + 32 * j] = h[j][s];
                         }
                     }
                 __syncwarp();

@@ -205,23 +205,23 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
-    if USE_TENSOR_CORES and not need_grad and st.stage == 'color' and st.weighting == 'distance':
-        # geometry branch (fp32 FFMA kernel, writes occupancy + has_nb) then the colour branch on tcgen05
-        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 0, cfg.r2_scalar)
-        L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                                   L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
-                                   L.ptr(has_nb), None, L.stream()), 'psl_decode_fwd[geometry]')
-        blob = _tc_blob(dev)
-        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
-        L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.stream()),
-                'psl_color_fwd_tc')
-        return raw, has_nb, None, pstruct
     save = None
     if need_grad:
         per = lib.psl_decode_save_floats_per_sample(C.byref(cfg))
         save = torch.empty(max(M * per, 1), dtype=torch.float32, device=dev)
+    if USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance':
+        # geometry branch (fp32 FFMA kernel: occupancy, has_nb, geometry activations) then the colour branch on tcgen05
+        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
+                           cfg.is_tracker, 0, cfg.r2_scalar)
+        L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                   L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
+                                   L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd[geometry]')
+        blob = _tc_blob(dev)
+        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.ptr(save),
+                                     L.stream()), 'psl_color_fwd_tc')
+        return raw, has_nb, save, pstruct
     L.check(lib.psl_decode_fwd(C.byref(cfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(rand_geo), L.ptr(rand_col),
                                L.ptr(affine), L.ptr(raw), L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd')

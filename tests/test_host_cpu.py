@@ -34,9 +34,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.DecodeCfg) == 40
     assert ctypes.sizeof(_lib.Grid) == 40       # 3 pointers + u32 + i32 + 2 floats
     cfg = _lib.DecodeCfg(1, 1, 0, 0, 2, 5, 0, 0, 0.0064)
-    assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 2944
+    assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 2304
     cfg.encode_rel_pos = 0
-    assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 1664
+    assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 1024
     cfg.stage = 0
     assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 352
 
