@@ -178,6 +178,8 @@ int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_params* params_h
                    const float* exposure_affine, const float* raw, const float* save, const float* d_raw,
                    float* d_pos, float* d_cg, float* wn, float* d_colpair,
                    const psl_decoder_grads* grads_host, float* d_exposure_affine,
+                   const float* dwn_extra /* (m,8) or NULL: added to dL/d(weights) */,
+                   const float* dpos_extra /* (m,3) or NULL: added to d_pos */,
                    void* ws, size_t ws_bytes, psl_stream_t stream);
 
 /* deterministic scatter of per-(sample,neighbour) feature gradients into dense (n_points,32) tensors
@@ -217,7 +219,22 @@ int psl_tc_pack_params(const psl_decoder_params* params_host, float* tc_blob, ps
 int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
                      const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos,
                      const float* col_feats, const float* rand_col, const float* exposure_affine, float* raw,
-                     float* save /* NULL, or the psl_decode_fwd save buffer (training) */, psl_stream_t stream);
+                     float* save /* NULL, or the psl_decode_fwd save buffer (FFMA backward) */,
+                     float* tsave /* NULL, or psl_tc_save_floats() floats (tensor-core backward) */, psl_stream_t stream);
+
+/* tensor-core training path of the colour branch: psl_color_fwd_tc(tsave) -> psl_color_bwd_tc (data gradients; the
+ * geometry branch, the IDW-weight gradient and d_pos are finished by psl_decode_bwd(stage = GEOMETRY, dwn_extra, dpos_extra)). */
+size_t psl_tc_fold_offset_floats(void);
+size_t psl_tc_bwd_blob_floats(void);
+size_t psl_tc_save_floats(int64_t m, int32_t encode_rel_pos);
+size_t psl_tc_bwd_tmp_floats(int64_t m, int32_t encode_rel_pos);
+int psl_tc_bwd_pack_params(const psl_decoder_params* params_host, const float* tc_blob, size_t tc_fold_offset_floats,
+                           float* bwd_blob, psl_stream_t stream);
+int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob, const float* pos, int64_t m, const int32_t* I,
+                     const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                     const float* exposure_affine, const float* raw, const float* d_raw, const float* tsave, float* tbwd,
+                     float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
+                     psl_stream_t stream);
 
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);

@@ -15,8 +15,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, 'libpointslam_b200.so')
-SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu']
-HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_tc.cuh']
+SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu']
+HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
 
@@ -68,7 +68,7 @@ _SIGS = {
                                  _vp, _vp, _vp, _vp, _vp]),
     'psl_decode_bwd': (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(DecoderParams), _vp, _vp, _i64, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(DecoderParams), _vp,
-                                 _vp, _sz, _vp]),
+                                 _vp, _vp, _vp, _sz, _vp]),
     'psl_feat_scatter_ws_bytes': (_sz, [_i64]),
     'psl_feat_scatter': (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'psl_composite_fwd': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
@@ -77,7 +77,14 @@ _SIGS = {
     'psl_ray_mask': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     'psl_tc_blob_floats': (_sz, []),
     'psl_tc_pack_params': (C.c_int, [C.POINTER(DecoderParams), _vp, _vp]),
-    'psl_color_fwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_color_fwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_tc_fold_offset_floats': (_sz, []),
+    'psl_tc_bwd_blob_floats': (_sz, []),
+    'psl_tc_save_floats': (_sz, [_i64, _i32]),
+    'psl_tc_bwd_tmp_floats': (_sz, [_i64, _i32]),
+    'psl_tc_bwd_pack_params': (C.c_int, [C.POINTER(DecoderParams), _vp, _sz, _vp, _vp]),
+    'psl_color_bwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp]),
     'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)

@@ -11,6 +11,7 @@
 // Replaces (forward only) MLP_color.get_feature_at_pos / forward, src/conv_onet/models/decoder.py:341-449.
 #include "psl_decode.cuh"
 #include "psl_tc.cuh"
+#include "psl_tc_layout.cuh"
 
 namespace psl {
 namespace ctc {
@@ -57,7 +58,8 @@ struct Args {
     const int* I; const float* D; const int* nnum; const double* r2;
     const float* cloud_pos; const float* col_feats; const float* rand_col; const float* affine;
     float* raw;                         // (m,4): xyz written here, w (occupancy) untouched
-    float* save;                        // training forward: pre-activations etc. for the backward (psl_decode.cuh SaveLayout)
+    float* save;                        // SAVE == 1: psl_decode.cuh SaveLayout (consumed by the FFMA backward)
+    float* tsave;                       // SAVE == 2: psl_tc_layout.cuh TSave (consumed by the tensor-core backward)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -149,7 +151,7 @@ __device__ __forceinline__ void worker_signal(uint64_t* a_ready) {
     tc::mbar_arrive(a_ready);
 }
 
-template <bool SAVE>
+template <int SAVE>
 __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sVec = reinterpret_cast<float*>(smem + SB_VEC);
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
     const bool rel = a.cfg.encode_rel_pos != 0;
     const SaveLayout SL = save_layout(1, a.cfg.encode_rel_pos);
     const long long M = a.m;
+    const TSave TL = tsave_layout(a.m, a.cfg.encode_rel_pos);
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
@@ -355,10 +358,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                         tc::tmem_ld32(lb + TP + c0, xv);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) xv[j] += b1[c0 + j];
-                        if (SAVE && inb) {
+                        if (SAVE == 1 && inb) {
                             float4* dst = reinterpret_cast<float4*>(a.save + SL.nz1 * M + (m * 8 + k) * 128 + c0);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) dst[q] = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
+                        }
+                        if (SAVE == 2) {
+                            float* dst = a.tsave + TL.z1T + ((tile * 8 + k) * 128 + c0) * 128 + r;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dst[j * 128] = xv[j];
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(xv[j]), xv[j], lo[j]);
@@ -372,8 +380,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     tc::tmem_ld16(lb + TSP + 16 * h, f);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] += b2[16 * h + j];
-                    if (SAVE && inb) {
-                        float4* dst = reinterpret_cast<float4*>(a.save + SL.nf * M + (m * 8 + k) * 32 + 16 * h);
+                    if ((SAVE == 1 && inb) || SAVE == 2) {
+                        float4* dst = SAVE == 1 ? reinterpret_cast<float4*>(a.save + SL.nf * M + (m * 8 + k) * 32 + 16 * h)
+                                                : reinterpret_cast<float4*>(a.tsave + TL.f + ((tile * 128 + r) * 8 + k) * 32 + 16 * h);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
                     }
@@ -396,10 +405,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                 float chi[16], clo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) cacc[j] = has ? cacc[j] : sRand[16 * h + j];
-                if (SAVE && inb) {
+                if (SAVE == 1 && inb) {
                     float4* dst = reinterpret_cast<float4*>(a.save + SL.cc * M + m * 32 + 16 * h);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dst[q] = make_float4(cacc[4 * q], cacc[4 * q + 1], cacc[4 * q + 2], cacc[4 * q + 3]);
+                }
+                if (SAVE == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a.tsave[TL.cT + (tile * 32 + 16 * h + j) * 128 + r] = cacc[j];
+                    if (h == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a.tsave[TL.wnT + (tile * 8 + k) * 128 + r] = wn[k];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) tc::split_tf32(cacc[j], chi[j], clo[j]);
@@ -430,10 +447,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     tc::tmem_ld32(lb + dcol + c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += bias[c0 + j];
-                    if (SAVE && inb) {
+                    if (SAVE == 1 && inb) {
                         float4* dst = reinterpret_cast<float4*>(a.save + SL.cz * M + ((long long)l * M + m) * 128 + c0);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                    if (SAVE == 2) {
+                        float* dst = a.tsave + TL.zT + (((long long)l * n_tiles + tile) * 128 + c0) * 128 + r;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[j * 128] = v[j];
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) tc::split_tf32(softplus100_fast(v[j]), v[j], lo[j]);
@@ -449,6 +471,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                 tc::tmem_ld16(lb + TQ, o);
                 if (h == 0 && inb) {
                     float cr = o[0] + sVec[V_BOUT], cg = o[1] + sVec[V_BOUT + 1], cb = o[2] + sVec[V_BOUT + 2];
+                    if (SAVE == 2) *reinterpret_cast<float4*>(a.tsave + TL.outpre + (tile * 128 + r) * 4) = make_float4(cr, cg, cb, 0.f);
                     if (a.cfg.rgb_mode == PSL_RGB_AFFINE_SIGMOID) {
                         const float* A = sRand + 32;
                         const float r2 = fmaf(cb, A[6], fmaf(cg, A[3], cr * A[0])) + A[9];
@@ -472,6 +495,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
 
 using namespace psl;
 
+extern "C" size_t psl_tc_fold_offset_floats(void) { return (size_t)ctc::TB_TOTAL; }
 extern "C" size_t psl_tc_blob_floats(void) { return (size_t)ctc::TB_TOTAL + (size_t)ctc::FOLD_FLOATS; }
 
 // fold + split + lay out the colour-branch weights for the tensor-core kernel (blob: psl_tc_blob_floats() floats)
@@ -492,25 +516,28 @@ extern "C" int psl_tc_pack_params(const psl_decoder_params* P, float* blob, psl_
 extern "C" int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m,
                                 const int32_t* I, const float* D, const int32_t* nnum, const double* r2,
                                 const float* cloud_pos, const float* col_feats, const float* rand_col,
-                                const float* exposure_affine, float* raw, float* save, psl_stream_t stream) {
+                                const float* exposure_affine, float* raw, float* save, float* tsave, psl_stream_t stream) {
     PSL_REQUIRE(cfg && tc_blob && pos && I && D && nnum && col_feats && rand_col && raw, "NULL argument");
     PSL_REQUIRE(!cfg->encode_rel_pos || cloud_pos, "rel-pos encoding needs cloud_pos");
     PSL_REQUIRE(cfg->rgb_mode != PSL_RGB_AFFINE_SIGMOID || exposure_affine, "affine mode needs exposure_affine");
     if (m == 0) return 0;
     ctc::Args a{};
     a.cfg = *cfg; a.blob = tc_blob; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
-    a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.save = save;
+    a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.save = save; a.tsave = tsave;
+    PSL_REQUIRE(!(save && tsave), "pass at most one of save / tsave");
     const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
     static bool attr_set = false;
     if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc::k_color_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
         attr_set = true;
     }
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     TimingScope ts(T_DECODE_FWD, as_stream(stream));
-    if (save) ctc::k_color_fwd_tc<true><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
-    else ctc::k_color_fwd_tc<false><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
+    if (tsave) ctc::k_color_fwd_tc<2><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
+    else if (save) ctc::k_color_fwd_tc<1><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
+    else ctc::k_color_fwd_tc<0><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

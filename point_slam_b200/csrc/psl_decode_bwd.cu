@@ -48,6 +48,8 @@ struct BwdArgs {
     const float* d_raw;
     float* d_pos; float* d_cg; float* wn_out; float* d_colpair; float* d_cc;
     float* partial;                     // [gridDim.x][GR_TOTAL]
+    const float* dwn_extra;             // (m,8)  dL/d(normalised weights) from another kernel (tensor-core colour branch)
+    const float* dpos_extra;            // (m,3)  dL/dpos from another kernel
     int want_geo_params, want_col_params;
 };
 
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
             sum += __shfl_xor_sync(0xffffffffu, sum, 4);
             const float den = fmaxf(sum, 1e-12f);
             const float wn = __fdiv_rn(w, den);
-            sWn[q] = wn; sWr[q] = w; sDWn[q] = 0.f;
+            sWn[q] = wn; sWr[q] = w; sDWn[q] = (a.dwn_extra && m < M) ? a.dwn_extra[m * 8 + k] : 0.f;
             sI[q] = (w != 0.f) ? idx : -1;
             if (k == 0) {
                 sHas[s] = (m < M) && (f.nnum[m] >= f.cfg.min_nn);
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
             const int s = lane >> 2, c = lane & 3;
             const long long m = m0 + s;
             sP[lane] = (m < M && c < 3) ? f.pos[m * 3 + c] : 0.f;
-            sDP[lane] = 0.f;
+            sDP[lane] = (a.dpos_extra && m < M && c < 3) ? a.dpos_extra[m * 3 + c] : 0.f;
             sDRaw[lane] = (m < M) ? a.d_raw[m * 4 + c] : 0.f;
         }
         __syncwarp();
@@ -923,7 +925,8 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
                               const double* r2, const float* cloud_pos, const float* geo_feats, const float* col_feats,
                               const float* exposure_affine, const float* raw, const float* save, const float* d_raw,
                               float* d_pos, float* d_cg, float* wn, float* d_colpair, const psl_decoder_grads* G,
-                              float* d_exposure_affine, void* ws, size_t ws_bytes, psl_stream_t stream) {
+                              float* d_exposure_affine, const float* dwn_extra, const float* dpos_extra, void* ws,
+                              size_t ws_bytes, psl_stream_t stream) {
     PSL_REQUIRE(cfg && P && pos && I && D && nnum && geo_feats && raw && save && d_raw && ws, "NULL argument");
     PSL_REQUIRE(m >= 0, "m < 0");
     const bool color = cfg->stage == PSL_STAGE_COLOR;
@@ -944,6 +947,7 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
     a.d_colpair = rel ? d_colpair : nullptr;
     a.d_cc = (color && !rel) ? d_colpair : nullptr;      // without the neighbour MLP the caller gets d_cc (m,32) here
     a.partial = static_cast<float*>(ws);
+    a.dwn_extra = dwn_extra; a.dpos_extra = dpos_extra;
     bool wg = false, wc = false;
     if (G) {
         wg = G->g_B || G->g_Wo || G->g_bo;

@@ -184,7 +184,16 @@ class RenderSettings:
                            self.min_nn, int(r2_group), int(self.is_tracker), 0, float(r2_scalar))
 
 
-USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch for inference (no-grad) renders
+USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
+USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
+_TC_BWD_BLOB = {}
+
+
+def _tc_bwd_blob(device):
+    key = str(device)
+    if key not in _TC_BWD_BLOB:
+        _TC_BWD_BLOB[key] = torch.empty(L.load().psl_tc_bwd_blob_floats(), dtype=torch.float32, device=device)
+    return _TC_BWD_BLOB[key]
 _TC_BLOB = {}
 
 
@@ -196,7 +205,8 @@ def _tc_blob(device):
 
 
 def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
-                    affine, need_grad):
+                    affine, need_grad, colour_param_grads=True):
+    """-> raw, has_nb, save (FFMA layout or None), tsave (tensor-core layout or None), param struct"""
     lib = L.load()
     dev = pos.device
     M = pos.shape[0]
@@ -205,11 +215,18 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
-    save = None
+    save = tsave = None
+    use_tc = USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance'
+    # tensor-core backward: data gradients only (weight gradients of the colour branch still need the FFMA kernel)
+    tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and not colour_param_grads
     if need_grad:
-        per = lib.psl_decode_save_floats_per_sample(C.byref(cfg))
+        scfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
+                           cfg.is_tracker, 0, cfg.r2_scalar) if tc_bwd else cfg
+        per = lib.psl_decode_save_floats_per_sample(C.byref(scfg))
         save = torch.empty(max(M * per, 1), dtype=torch.float32, device=dev)
-    if USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance':
+        if tc_bwd:
+            tsave = torch.empty(lib.psl_tc_save_floats(M, cfg.encode_rel_pos), dtype=torch.float32, device=dev)
+    if use_tc:
         # geometry branch (fp32 FFMA kernel: occupancy, has_nb, geometry activations) then the colour branch on tcgen05
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 0, cfg.r2_scalar)
@@ -219,17 +236,17 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         blob = _tc_blob(dev)
         L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
         L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.ptr(save),
-                                     L.stream()), 'psl_color_fwd_tc')
-        return raw, has_nb, save, pstruct
+                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
+                                     None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
+        return raw, has_nb, save, tsave, pstruct
     L.check(lib.psl_decode_fwd(C.byref(cfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(rand_geo), L.ptr(rand_col),
                                L.ptr(affine), L.ptr(raw), L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd')
-    return raw, has_nb, save, pstruct
+    return raw, has_nb, save, None, pstruct
 
 
 def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, cloud_pos, geo, col, affine, raw, save,
-                     d_raw, want_pos, want_geo, want_col, want_affine):
+                     d_raw, want_pos, want_geo, want_col, want_affine, tsave=None):
     """-> (d_pos, d_geo, d_col, param grads list, d_affine)"""
     lib = L.load()
     dev = pos.device
@@ -257,10 +274,35 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
     ws_bytes = lib.psl_decode_bwd_ws_bytes(M)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     packed = _packed_buffer(dev)
-    L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
-                               L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
-                               L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), L.ptr(wn), L.ptr(d_colpair),
-                               C.byref(gstruct), L.ptr(d_aff), L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
+    if tsave is not None:
+        # colour branch on tensor cores (data gradients), then geometry branch + IDW weights + d_pos on the FFMA kernel
+        blob, bblob = _tc_blob(dev), _tc_bwd_blob(dev)
+        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(blob), lib.psl_tc_fold_offset_floats(), L.ptr(bblob), L.stream()),
+                'psl_tc_bwd_pack_params')
+        tbwd = torch.empty(lib.psl_tc_bwd_tmp_floats(M, cfg.encode_rel_pos), dtype=torch.float32, device=dev)
+        if wn is None:
+            wn = torch.empty((M, 8), dtype=torch.float32, device=dev)
+        dwn_col = torch.empty((M, 8), dtype=torch.float32, device=dev)
+        dpos_col = torch.empty((M, 3), dtype=torch.float32, device=dev) if want_pos else None
+        L.check(lib.psl_color_bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
+                                     L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col), 0, None,
+                                     L.stream()), 'psl_color_bwd_tc')
+        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
+                           cfg.is_tracker, 0, cfg.r2_scalar)
+        L.check(lib.psl_decode_bwd(C.byref(gcfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
+                                   L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), None, None, L.ptr(raw),
+                                   L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), None, None,
+                                   C.byref(gstruct), None, L.ptr(dwn_col), L.ptr(dpos_col), L.ptr(ws), ws_bytes, L.stream()),
+                'psl_decode_bwd[geometry]')
+        if want_affine:
+            d_aff = None          # (affine-coefficient gradients need the weight-gradient pass: not on this path)
+    else:
+        L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
+                                   L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
+                                   L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), L.ptr(wn), L.ptr(d_colpair),
+                                   C.byref(gstruct), L.ptr(d_aff), None, None, L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
     d_geo = d_col = None
     if want_geo or want_col:
         d_geo = torch.zeros_like(geo) if want_geo else None
@@ -304,8 +346,10 @@ class _RenderFn(torch.autograd.Function):
                                      L.stream()), 'psl_raymarch_knn')
         cfg = st.cfg(S, r2s)
         need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
-        raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
-                                               rand_col, aff, need_grad)
+        nig = ctx.needs_input_grad
+        cpg = any(n and name.startswith('c_') for n, name in zip(nig[13:], L_PARAM_NAMES)) or bool(nig[12])
+        raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
+                                                      rand_col, aff, need_grad, colour_param_grads=cpg)
         depth = torch.empty((R,), dtype=torch.float32, device=dev)
         var = torch.empty((R,), dtype=torch.float32, device=dev)
         rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
@@ -314,7 +358,7 @@ class _RenderFn(torch.autograd.Function):
         ray_mask = torch.empty((R,), dtype=torch.uint8, device=dev)
         L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
         ctx.st, ctx.cfg, ctx.n_params = st, cfg, len(params)
-        ctx.save_for_backward(z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, *params_c)
+        ctx.save_for_backward(z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave, *params_c)
         ctx.mark_non_differentiable(ray_mask)
         return depth, var, rgb, ray_mask.bool()
 
@@ -322,8 +366,8 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, d_depth, d_var, d_rgb, _d_mask):
         lib = L.load()
         st, cfg = ctx.st, ctx.cfg
-        z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save = ctx.saved_tensors[:13]
-        params = list(ctx.saved_tensors[13:])
+        z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave = ctx.saved_tensors[:14]
+        params = list(ctx.saved_tensors[14:])
         R, S = z_vals.shape
         dev = z_vals.device
         d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
@@ -336,7 +380,8 @@ class _RenderFn(torch.autograd.Function):
         want_pos = nig[8] or nig[9]
         needs = list(nig[13:])
         d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, cfg, params, needs, pos, I, D, nn, r2_ray, cloud, geo,
-                                                             col, aff, raw, save, d_raw, want_pos, nig[10], nig[11], nig[12])
+                                                             col, aff, raw, save, d_raw, want_pos, nig[10], nig[11], nig[12],
+                                                             tsave=tsave)
         d_o = d_d = None
         if want_pos:
             d_o = torch.empty((R, 3), dtype=torch.float32, device=dev) if nig[8] else None
@@ -363,10 +408,12 @@ class _DecodeFn(torch.autograd.Function):
         r2s = float(np.float32(st.radius_query ** 2))
         cfg = st.cfg(r2_group, r2s)
         need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
-        raw, has_nb, save, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_pts, cloud, geo, col, rand_geo,
-                                               rand_col, aff, need_grad)
+        nig = ctx.needs_input_grad
+        cpg = any(n and name.startswith('c_') for n, name in zip(nig[11:], L_PARAM_NAMES)) or bool(nig[10])
+        raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_pts, cloud, geo, col, rand_geo,
+                                                      rand_col, aff, need_grad, colour_param_grads=cpg)
         ctx.st, ctx.cfg = st, cfg
-        ctx.save_for_backward(pos, I, D, nn, r2_pts, cloud, geo, col, aff, raw, save, *params_c)
+        ctx.save_for_backward(pos, I, D, nn, r2_pts, cloud, geo, col, aff, raw, save, tsave, *params_c)
         hb = has_nb.bool()
         ctx.mark_non_differentiable(hb)
         return raw, hb
@@ -374,12 +421,12 @@ class _DecodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_raw, _d_mask):
         st, cfg = ctx.st, ctx.cfg
-        pos, I, D, nn, r2, cloud, geo, col, aff, raw, save = ctx.saved_tensors[:11]
-        params = list(ctx.saved_tensors[11:])
+        pos, I, D, nn, r2, cloud, geo, col, aff, raw, save, tsave = ctx.saved_tensors[:12]
+        params = list(ctx.saved_tensors[12:])
         nig = ctx.needs_input_grad            # (st, grid, r2, r2_group, rand_geo, rand_col, cloud, p, geo, col, affine, *params)
         d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, cfg, params, list(nig[11:]), pos, I, D, nn, r2, cloud,
                                                              geo, col, aff, raw, save, _f32c(d_raw), nig[7], nig[8],
-                                                             nig[9], nig[10])
+                                                             nig[9], nig[10], tsave=tsave)
         return (None, None, None, None, None, None, None, d_pos, d_geo, d_col, d_aff if nig[10] else None, *grads)
 
 

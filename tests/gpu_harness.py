@@ -41,8 +41,9 @@ def build_objects(c, scene=None):
     return cfg, decoders, npc, renderer
 
 
-def run_case_gpu(c, objects=None):
+def run_case_gpu(c, objects=None, freeze_decoders=False):
     cfg, decoders, npc, renderer = objects or build_objects(c)
+    decoders.requires_grad_(not freeze_decoders)
     intr = C.INTR
     t = lambda k, dt=torch.float32: torch.from_numpy(np.asarray(c[k])).to(device=DEV, dtype=dt)
     gt_depth, gt_color = t('gt_depth'), t('gt_color')

@@ -68,3 +68,31 @@ def test_color_branch_on_tensor_cores_matches_oracle(name):
     e_32 = C.rel_err(o32['color'], o64['color'])
     print(f'{name}: colour rel err vs fp64  tcgen05 {e_tc:.2e}  ffma {e_ff:.2e}  fp32 oracle {e_32:.2e}')
     assert e_tc <= max(1e-4, 3 * e_32)
+
+
+@pytest.mark.parametrize('name', ['tracker_color', 'tum_tracker', 'mapper_color', 'tum_near_pcl', 's32_color', 'fixed_radius_zero_depth'])
+def test_tensor_core_backward_data_path(name):
+    """With the decoder frozen (what the tracker needs) the colour branch runs forward AND backward on tcgen05
+    (psl_color_fwd_tc -> psl_color_bwd_tc): pose and feature gradients against the fp64 oracle."""
+    from point_slam_b200 import ops
+    from tests import cases as C
+    from tests.gpu_harness import run_case_gpu
+    c = C.load_case(name)
+    o32, o64 = C.run_oracle(c, torch.float32), C.run_oracle(c, torch.float64)
+    assert ops.USE_TENSOR_CORES and ops.USE_TC_BACKWARD
+    got = run_case_gpu(c, freeze_decoders=True)
+    ops.USE_TC_BACKWARD = False
+    ref = run_case_gpu(c, freeze_decoders=True)                     # same forward, FFMA backward
+    ops.USE_TC_BACKWARD = True
+
+    def tol(what, g, a32, a64):
+        e, e32 = C.rel_err(g.cpu(), a64), C.rel_err(a32, a64)
+        print(f'{name} {what}: tcgen05 {e:.2e}  fp32 oracle {e32:.2e}')
+        assert e <= max(1e-4, 3 * e32), what
+    tol('loss', got['loss'], o32['loss'], o64['loss'])
+    if 'grad_cam' in o64:
+        tol('pose grad', got['grad_cam'], o32['grad_cam'], o64['grad_cam'])
+        assert not torch.equal(got['grad_cam'], ref['grad_cam']), 'tensor-core backward was not taken'
+    tol('geo feature grad', got['grad_geo'], o32['grad_geo'], o64['grad_geo'])
+    tol('col feature grad', got['grad_col'], o32['grad_col'], o64['grad_col'])
+    assert not got['grad_params']
