@@ -236,6 +236,13 @@ int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob, const flo
                      float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
                      psl_stream_t stream);
 
+/* weight gradients of the colour branch (GEMMs over the sample index) from the buffers left by psl_color_fwd_tc(tsave) and
+ * psl_color_bwd_tc(want_wgrad = 1); only the c_* entries of `grads_host` are written.  ws: psl_wgrad_tc_ws_floats(m). */
+size_t psl_wgrad_tc_ws_floats(int64_t m);
+int psl_wgrad_tc(const psl_decode_cfg* cfg, const psl_decoder_params* params_host, const float* pos, int64_t m, const int32_t* I,
+                 const float* cloud_pos, const float* col_feats, const float* tsave, const float* tbwd, int32_t n_cta_bwd,
+                 const psl_decoder_grads* grads_host, float* d_exposure_affine, float* ws, size_t ws_floats, psl_stream_t stream);
+
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
 

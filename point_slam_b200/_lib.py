@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, 'libpointslam_b200.so')
-SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu']
+SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu', 'psl_wgrad_tc.cu']
 HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
@@ -78,6 +78,9 @@ _SIGS = {
     'psl_tc_blob_floats': (_sz, []),
     'psl_tc_pack_params': (C.c_int, [C.POINTER(DecoderParams), _vp, _vp]),
     'psl_color_fwd_tc': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_wgrad_tc_ws_floats': (_sz, [_i64]),
+    'psl_wgrad_tc': (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(DecoderParams), _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32,
+                               C.POINTER(DecoderParams), _vp, _vp, _sz, _vp]),
     'psl_tc_fold_offset_floats': (_sz, []),
     'psl_tc_bwd_blob_floats': (_sz, []),
     'psl_tc_save_floats': (_sz, [_i64, _i32]),

@@ -186,6 +186,7 @@ class RenderSettings:
 
 USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
+USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
 _TC_BWD_BLOB = {}
 
 
@@ -217,8 +218,8 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
     save = tsave = None
     use_tc = USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance'
-    # tensor-core backward: data gradients only (weight gradients of the colour branch still need the FFMA kernel)
-    tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and not colour_param_grads
+    # tensor-core backward (data gradients + weight gradients of the colour branch; geometry branch on the FFMA kernel)
+    tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and (USE_TC_WGRAD or not colour_param_grads)
     if need_grad:
         scfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 0, cfg.r2_scalar) if tc_bwd else cfg
@@ -285,10 +286,18 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
             wn = torch.empty((M, 8), dtype=torch.float32, device=dev)
         dwn_col = torch.empty((M, 8), dtype=torch.float32, device=dev)
         dpos_col = torch.empty((M, 3), dtype=torch.float32, device=dev) if want_pos else None
+        want_cparams = any(w and name.startswith('c_') for w, name in zip(want, L_PARAM_NAMES))
+        grid_a = C.c_int32(0)
         L.check(lib.psl_color_bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                      L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
-                                     L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col), 0, None,
-                                     L.stream()), 'psl_color_bwd_tc')
+                                     L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
+                                     int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')
+        if want_cparams or want_affine:
+            wsf = lib.psl_wgrad_tc_ws_floats(M)
+            wws = torch.empty(wsf, dtype=torch.float32, device=dev)
+            L.check(lib.psl_wgrad_tc(C.byref(cfg), C.byref(pstruct), L.ptr(pos), M, L.ptr(I), L.ptr(cloud_pos), L.ptr(col),
+                                     L.ptr(tsave), L.ptr(tbwd), grid_a.value, C.byref(gstruct), L.ptr(d_aff), L.ptr(wws), wsf,
+                                     L.stream()), 'psl_wgrad_tc')
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 0, cfg.r2_scalar)
         L.check(lib.psl_decode_bwd(C.byref(gcfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
@@ -296,8 +305,6 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
                                    L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), None, None,
                                    C.byref(gstruct), None, L.ptr(dwn_col), L.ptr(dpos_col), L.ptr(ws), ws_bytes, L.stream()),
                 'psl_decode_bwd[geometry]')
-        if want_affine:
-            d_aff = None          # (affine-coefficient gradients need the weight-gradient pass: not on this path)
     else:
         L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
                                    L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
