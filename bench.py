@@ -257,10 +257,20 @@ def run_ours(args):
     tot_kernel_ms = sum(v[0] for v in prof.values())
     top = max(prof, key=lambda k: prof[k][0])
     top_ms, top_n = prof[top]
-    # samples one launch of the dominant kernel processes: tracker launches see ~TRACK_PIX*S, mapper ~MAP_PIX*S
-    per_launch_samples = n_prof / max(prof['decode_fwd'][1], 1)
-    bytes_per_sample = ALGO_BYTES_BWD if top == 'decode_bwd' else ALGO_BYTES_FWD
+    # samples one launch of the dominant kernel processes (tracker launches see ~TRACK_PIX*S, mapper ~MAP_PIX*S)
+    per_launch_samples = n_prof / max(prof['knn'][1], 1)
+    if top in ('wgrad_tc',):
+        per_launch_samples = MAP_PIX * S                                   # only the mapper's colour-stage iterations launch it
+    bytes_per_sample = {'decode_bwd': ALGO_BYTES_BWD, 'color_bwd_tc': ALGO_BYTES_BWD, 'wgrad_tc': ALGO_BYTES_BWD}.get(top, ALGO_BYTES_FWD)
     achieved = per_launch_samples * bytes_per_sample / (top_ms / max(top_n, 1) * 1e-3) / 1e9
+    # tensor-core view of the same kernel: algorithmic FLOPs of the colour branch (fwd 2 x (96 700 + 86 256) MAC; bwd-data and wgrad the same)
+    tc_flops = {'color_fwd_tc': 2 * 182956, 'color_bwd_tc': 2 * 182956, 'wgrad_tc': 2 * 182956}.get(top)
+    tensor = None
+    if tc_flops:
+        tf = per_launch_samples * tc_flops / (top_ms / max(top_n, 1) * 1e-3) / 1e12
+        tensor = {'achieved_tflops_fp32_equivalent': tf, 'mma_tflops_issued_3xtf32': 3 * tf,
+                  'peak_bf16_tflops': float(peaks.get('bf16_tflops', 1590.0)), 'frac_of_bf16_peak_issued': 3 * tf / float(peaks.get('bf16_tflops', 1590.0)),
+                  'note': 'kind::tf32 runs at half the bf16 rate; 3 MMAs per fp32-accurate product'}
     traffic = None
     tj = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tj):
@@ -286,7 +296,7 @@ def run_ours(args):
                      'algorithmic_bytes_per_sample': bytes_per_sample, 'samples_per_launch': per_launch_samples,
                      'avg_launch_ms': top_ms / max(top_n, 1),
                      'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
-                     'fp32_tflops_fwd_bwd': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12},
+                     'fp32_tflops_fwd_bwd': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12, 'tensor': tensor},
         'step_ms': [round(x, 1) for x in per_step], 'step_ms_e2e': [round(x, 1) for x in per_step_e2e],
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},

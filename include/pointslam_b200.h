@@ -47,8 +47,9 @@ int psl_device_sm_count(void);
 /* optional device timing: when enabled, every kernel launch made by the library is bracketed by CUDA events on the
  * launching stream; psl_timing_collect synchronises the device and returns summed milliseconds / launch counts per
  * kernel family: 0 knn, 1 decode_fwd, 2 decode_bwd, 3 composite/ray kernels, 4 feature scatter, 5 param pack,
- * 6 partial-gradient reduce (arrays of PSL_TIMING_SLOTS entries). */
-#define PSL_TIMING_SLOTS 7
+ * 6 partial-gradient reduce, 7 colour forward (tcgen05), 8 colour backward data (tcgen05), 9 colour weight gradients
+ * (tcgen05) (arrays of PSL_TIMING_SLOTS entries). */
+#define PSL_TIMING_SLOTS 10
 /* kernels launched by this process through the library so far (bench.py's gpu_launches) */
 unsigned long long psl_launch_count(void);
 int psl_timing_enable(int on);

@@ -152,7 +152,7 @@ def ptr(t, dtype=None):
     return C.c_void_p(t.data_ptr())
 
 
-TIMING_NAMES = ['knn', 'decode_fwd', 'decode_bwd', 'composite', 'scatter', 'pack', 'reduce']
+TIMING_NAMES = ['knn', 'decode_fwd', 'decode_bwd', 'composite', 'scatter', 'pack', 'reduce', 'color_fwd_tc', 'color_bwd_tc', 'wgrad_tc']
 
 
 def timing_enable(on: bool):

@@ -540,7 +540,7 @@ extern "C" int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob
     }
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (grid_out) *grid_out = (int32_t)grid;
-    TimingScope ts(T_DECODE_BWD, as_stream(stream));
+    TimingScope ts(T_COLOR_BWD_TC, as_stream(stream));
     cbt::k_color_bwd_tc<<<(unsigned)grid, cbt::NTHR, cbt::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -534,7 +534,7 @@ extern "C" int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob,
         attr_set = true;
     }
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    TimingScope ts(T_DECODE_FWD, as_stream(stream));
+    TimingScope ts(T_COLOR_FWD_TC, as_stream(stream));
     if (tsave) ctc::k_color_fwd_tc<2><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
     else if (save) ctc::k_color_fwd_tc<1><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);
     else ctc::k_color_fwd_tc<0><<<(unsigned)grid, ctc::NTHR, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);

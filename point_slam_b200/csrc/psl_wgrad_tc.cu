@@ -506,7 +506,7 @@ extern "C" int psl_wgrad_tc(const psl_decode_cfg* cfg, const psl_decoder_params*
     }
     float* sums = ws + (size_t)wgt::W_TOTAL * grid;
     {
-        TimingScope ts(T_DECODE_BWD, st);
+        TimingScope ts(T_WGRAD_TC, st);
         wgt::k_wgrad_tc<<<(unsigned)grid, wgt::NTHR, wgt::SB_TOTAL, st>>>(a, n_tiles);
         PSL_CHECK_CUDA(cudaGetLastError());
     }

@@ -126,7 +126,7 @@ class GraphedTracker:
         self.depth = torch.zeros(H, W, device=device)
         self.dyn = torch.zeros(H, W, dtype=torch.float64, device=device)
         self.cam = torch.zeros(7, device=device, requires_grad=True)
-        self.opt = torch.optim.Adam([self.cam], lr=lr, capturable=True)
+        self.opt = torch.optim.Adam([self.cam], lr=lr, capturable=True, fused=True)
         self.loss = torch.zeros((), device=device)
         self.graph = None
 
@@ -214,7 +214,7 @@ class GraphedMapper:
         st.col = torch.zeros(self.u_max, 32, device=d, requires_grad=True)
         st.optimizer = torch.optim.Adam([{'params': list(self.dec.color_decoder.parameters()), 'lr': self.lrs[0]},
                                          {'params': [st.geo], 'lr': self.lrs[1]}, {'params': [st.col], 'lr': self.lrs[2]}],
-                                        capturable=True)
+                                        capturable=True, fused=True)
         self.state = st
         self.keyframes = dict(color=torch.zeros(n_kf, H, W, 3, device=d), depth=torch.zeros(n_kf, H, W, device=d),
                               c2w=torch.zeros(n_kf, 3, 4, device=d), dyn_r_query=torch.zeros(n_kf, H, W, dtype=torch.float64, device=d))

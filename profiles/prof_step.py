@@ -1,4 +1,5 @@
-"""Profiling driver: the bench scene, a few tracker / mapper iterations inside a cudaProfilerStart/Stop window.
+"""Profiling driver: the bench scene, a few tracking / mapping iterations (the static-shape shells that bench.py replays as
+CUDA graphs, launched eagerly here so that ncu sees every kernel) inside a cudaProfilerStart/Stop window.
 
     ncu --profile-from-start off ... python profiles/prof_step.py [n_track n_map]
 """
@@ -16,23 +17,25 @@ n_track = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n_map = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = 'cuda:0'
 scene = bench.GpuScene(0, dev, 500000, 1)
-cur = scene.resident[0]
-npc, dec, render = scene.npc, scene.decoders, scene.renderer.render_batch_ray
-cloud = npc.cloud_pos_tensor()
-cam = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.01, scene.rng).to(dev).requires_grad_(True)
-opt = torch.optim.Adam([cam], lr=0.002)
-idx = IT.frustum_indices(cloud, cur['c2w'], bench.INTR)
-state = IT.MapperState(npc, dec, idx)
-kfs = [cur] + scene.keyframes
+fh = scene.frames_host[bench.N_KEYFRAMES]
+src = scene.resident[0]
+tr, mp = scene.tracker, scene.mapper
+tr.load_frame(src['color'], src['depth'], src['dyn_r_query'], bench.cam_tensor_from_c2w(fh['c2w'], 0.01, scene.rng).to(dev))
+cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=src['c2w'])
+idx = IT.frustum_indices(scene.npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
+mp.begin_frame(idx, [cur] + scene.keyframes)
 
 
 def run(nt, nm):
+    flags = [(p, p.requires_grad) for p in scene.decoders.parameters()]
+    for p, _ in flags:
+        p.requires_grad_(False)
     for _ in range(nt):
-        IT.tracker_iteration(render, npc, dec, cam, opt, cur['color'], cur['depth'], cur['dyn_r_query'], bench.INTR,
-                             bench.TRACK_PIX, dev, npc.get_geo_feats(), npc.get_col_feats(), cloud, edge=(100, 100))
+        tr._iter()
+    for p, f in flags:
+        p.requires_grad_(f)
     for it in range(nm):
-        IT.mapper_iteration(render, npc, dec, state, kfs, bench.INTR, bench.MAP_PIX, dev,
-                            'geometry' if it % 2 == 0 else 'color', cloud)
+        mp._iter('geometry' if it % 2 == 0 else 'color')
 
 
 run(2, 2)                      # warm-up (lazy init, allocator)
