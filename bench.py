@@ -142,8 +142,8 @@ class GpuScene:
         self.out_host = torch.empty(8, dtype=torch.float32).pin_memory()
         from point_slam_b200 import graphed as G
         self.G = G
-        self.tracker = G.GraphedTracker(self.renderer, self.npc, self.decoders, INTR, TRACK_PIX, device, edge=(100, 100))
-        self.mapper = G.GraphedMapper(self.renderer, self.npc, self.decoders, INTR, MAP_PIX, device)
+        self.tracker = G.FusedTracker(self.renderer, self.npc, self.decoders, INTR, TRACK_PIX, device, edge=(100, 100))
+        self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, MAP_PIX, device)
 
     def _to_device(self, f):
         d = self.device
@@ -165,13 +165,8 @@ class GpuScene:
         if graphs:
             loss = tr.run(TRACK_ITERS)
         else:
-            flags = [(p, p.requires_grad) for p in dec.parameters()]
-            for p, _ in flags:
-                p.requires_grad_(False)
             for _ in range(TRACK_ITERS):
                 tr._iter()
-            for p, f in flags:
-                p.requires_grad_(f)
             loss = tr.loss
         cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn,
                    c2w=torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True))
@@ -284,7 +279,7 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'C2 Replica-office0-like frame: 40 track it x 1500 rays + 60 map it x 5000 rays, S=5, '
                                f'{args.points} pts, 640x480; one scene per GPU', 'points': args.points,
-                   'work_per_step': 'fwd + loss + bwd + Adam (tracker pose; mapper features + colour decoder); every iteration is one CUDA-graph replay of a static-shape shell',
+                   'work_per_step': 'pixel sampling + render fwd + loss + bwd + Adam (tracker pose; mapper feature rows + colour decoder); every iteration is one CUDA-graph replay of a static-shape shell of library kernels (point_slam_b200/graphed.py: FusedTracker / FusedMapper)',
                    'l2': 'inputs larger than L2 (cloud+features 134 MB, saved activations ~290 MB / mapper iteration)',
                    'parallelism': f'scene-per-gpu x{world}'},
         'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes, 'd2h_bytes_per_step': 32,

@@ -48,8 +48,8 @@ int psl_device_sm_count(void);
  * launching stream; psl_timing_collect synchronises the device and returns summed milliseconds / launch counts per
  * kernel family: 0 knn, 1 decode_fwd, 2 decode_bwd, 3 composite/ray kernels, 4 feature scatter, 5 param pack,
  * 6 partial-gradient reduce, 7 colour forward (tcgen05), 8 colour backward data (tcgen05), 9 colour weight gradients
- * (tcgen05) (arrays of PSL_TIMING_SLOTS entries). */
-#define PSL_TIMING_SLOTS 10
+ * (tcgen05), 10 iteration-shell kernels (arrays of PSL_TIMING_SLOTS entries). */
+#define PSL_TIMING_SLOTS 11
 /* kernels launched by this process through the library so far (bench.py's gpu_launches) */
 unsigned long long psl_launch_count(void);
 int psl_timing_enable(int on);
@@ -191,6 +191,13 @@ int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, const float*
                      const float* d_colpair, const float* d_cc, float* d_geo, float* d_col,
                      void* ws, size_t ws_bytes, psl_stream_t stream);
 
+/* same, into a compact (n_rows,32) gradient of a SUBSET of the points: row_map (n_points) gives the output row of a point or
+ * -1 (its pairs are dropped) -- the frustum-selected slices Mapper.optimize_map optimises (Mapper.py:345-414) without the
+ * dense index_put / gather round trip.  n_rows replaces n_points as the row count of d_geo / d_col. */
+int psl_feat_scatter_mapped(const int32_t* I, int64_t m, const int32_t* row_map, int64_t n_rows, const float* wn,
+                            const float* d_cg, const float* d_colpair, const float* d_cc, float* d_geo, float* d_col,
+                            void* ws, size_t ws_bytes, psl_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * alpha composite      replaces: raw2outputs_nerf_color (src/common.py:298-336) + the -100 masking of
  *                      Renderer.py:189-190 (mask applied to the VALUE only, gradient passes through)
@@ -243,6 +250,38 @@ size_t psl_wgrad_tc_ws_floats(int64_t m);
 int psl_wgrad_tc(const psl_decode_cfg* cfg, const psl_decoder_params* params_host, const float* pos, int64_t m, const int32_t* I,
                  const float* cloud_pos, const float* col_feats, const float* tsave, const float* tbwd, int32_t n_cta_bwd,
                  const psl_decoder_grads* grads_host, float* d_exposure_affine, float* ws, size_t ws_floats, psl_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * iteration shell       the per-iteration glue of the two callers as single kernels (no data-dependent shapes, no host
+ *                       synchronisation, fixed-order reductions), so that one optimisation iteration is ~20 launches
+ *                       and can be replayed as a CUDA graph.
+ * ------------------------------------------------------------------------- */
+/* pixel sampling -> rays.  pix (n_frames*per_frame) int64: index into the (H - 2*H0... ) window, row = pix / win_w + H0,
+ * column = pix % win_w + W0 (common.get_sample_uv, common.py:77-89).  Pose: `cam` (7) = [quaternion w,x,y,z (not normalised), T]
+ * (common.get_camera_from_tensor, common.py:225-267) for ONE frame, or `c2w` (n_frames,3,4).  Outputs: rays_o/rays_d
+ * (common.get_rays_from_uv, common.py:40-56), the sampled depth / colour and r2 = dyn_radius^2 (float64, may be NULL). */
+int psl_sample_rays(const int64_t* pix, int32_t n_frames, int32_t per_frame, int32_t H, int32_t W, int32_t H0, int32_t W0,
+                    int32_t win_w, const float* cam, const float* c2w, const float* color /* (n_frames,H,W,3) */,
+                    const float* depth /* (n_frames,H,W) */, const double* dyn_radius /* (n_frames,H,W) or NULL */,
+                    float fx, float fy, float cx, float cy, float* rays_o, float* rays_d, float* b_depth, float* b_color,
+                    double* r2, psl_stream_t stream);
+/* inside = depth > 0 and depth <= min(10 * median(depth > 0), 1.2 * max(depth))  (Tracker.py:142-148, Mapper.py:507-513);
+ * depth_in = depth where inside else 0 (rays that the reference compacts away stay in the batch with zero weight). n <= 8192 */
+int psl_depth_gate(const float* b_depth, int32_t n, float* depth_in, uint8_t* inside, psl_stream_t stream);
+/* loss AND its gradient w.r.t. the rendered depth / colour.  mode 0 = tracking (Tracker.py:158-180, uncertainty-normalised,
+ * 10x-mean outlier mask, clamp 1e3), mode 1 = mapping (Mapper.py:524-552).  d_rgb NULL: depth term only (geometry stage). */
+int psl_shell_loss(int32_t mode, int32_t n, const float* depth_in, const uint8_t* inside, const uint8_t* ray_mask,
+                   const float* depth, const float* var, const float* rgb, const float* b_color, float w_color,
+                   float* loss, float* d_depth, float* d_rgb, psl_stream_t stream);
+/* chain rule of psl_sample_rays(cam): (d_rays_o, d_rays_d) (n,3) -> d_cam (7) */
+int psl_pose_bwd(const int64_t* pix, int32_t n, int32_t H0, int32_t W0, int32_t win_w, float fx, float fy, float cx, float cy,
+                 const float* cam, const float* d_rays_o, const float* d_rays_d, float* d_cam, psl_stream_t stream);
+/* torch.optim.Adam step (no weight decay / amsgrad) on `n_slots` rows of width `width`: slot u updates row rows[u] of `param`
+ * (rows NULL: row u; rows[u] < 0: skipped) from grad/exp_avg/exp_avg_sq (n_slots,width); `step` (device int) is incremented
+ * first.  zero_grad != 0 clears the consumed gradient (so that psl_feat_scatter_mapped finds a zeroed buffer). */
+int psl_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int64_t* rows, int64_t n_slots,
+                  int32_t width, int32_t* step, float lr, float beta1, float beta2, float eps, int32_t zero_grad,
+                  psl_stream_t stream);
 
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, 'libpointslam_b200.so')
-SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu', 'psl_wgrad_tc.cu']
+SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu']
 HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
@@ -71,6 +71,13 @@ _SIGS = {
                                  _vp, _vp, _vp, _sz, _vp]),
     'psl_feat_scatter_ws_bytes': (_sz, [_i64]),
     'psl_feat_scatter': (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'psl_feat_scatter_mapped': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'psl_sample_rays': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32,
+                                  _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_depth_gate': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    'psl_shell_loss': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    'psl_pose_bwd': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    'psl_adam_rows': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _f32, _f32, _i32, _vp]),
     'psl_composite_fwd': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_composite_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_rays_bwd': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
@@ -152,7 +159,7 @@ def ptr(t, dtype=None):
     return C.c_void_p(t.data_ptr())
 
 
-TIMING_NAMES = ['knn', 'decode_fwd', 'decode_bwd', 'composite', 'scatter', 'pack', 'reduce', 'color_fwd_tc', 'color_bwd_tc', 'wgrad_tc']
+TIMING_NAMES = ['knn', 'decode_fwd', 'decode_bwd', 'composite', 'scatter', 'pack', 'reduce', 'color_fwd_tc', 'color_bwd_tc', 'wgrad_tc', 'shell']
 
 
 def timing_enable(on: bool):

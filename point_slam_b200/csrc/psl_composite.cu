@@ -117,11 +117,14 @@ __global__ void k_ray_mask(const unsigned char* __restrict__ has_nb, long long R
 }
 
 // ---- deterministic feature-gradient scatter ----------------------------------------------------------------
+// key = output row of the pair: the point index, or row_map[point] when only a subset of rows is optimised (pairs of
+// unmapped points, row_map < 0, are dropped together with the zero-weight ones)
 __global__ void k_pair_keys(const int* __restrict__ I, const float* __restrict__ wn, long long n_pairs, unsigned n_points,
-                            unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+                            const int* __restrict__ row_map, unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
-    const int idx = I[p];
+    int idx = I[p];
+    if (idx >= 0 && row_map) idx = row_map[idx];
     keys[p] = (idx >= 0 && wn[p] != 0.f) ? (unsigned)idx : n_points;
     vals[p] = (unsigned)p;
 }
@@ -214,6 +217,12 @@ extern "C" size_t psl_feat_scatter_ws_bytes(int64_t m) {
 extern "C" int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, const float* wn, const float* d_cg,
                                 const float* d_colpair, const float* d_cc, float* d_geo, float* d_col, void* ws,
                                 size_t ws_bytes, psl_stream_t stream) {
+    return psl_feat_scatter_mapped(I, m, nullptr, n_points, wn, d_cg, d_colpair, d_cc, d_geo, d_col, ws, ws_bytes, stream);
+}
+
+extern "C" int psl_feat_scatter_mapped(const int32_t* I, int64_t m, const int32_t* row_map, int64_t n_points, const float* wn,
+                                       const float* d_cg, const float* d_colpair, const float* d_cc, float* d_geo, float* d_col,
+                                       void* ws, size_t ws_bytes, psl_stream_t stream) {
     PSL_REQUIRE(I && wn && ws, "NULL argument");
     PSL_REQUIRE(!d_geo || d_cg, "d_geo needs d_cg");
     PSL_REQUIRE(!d_col || d_colpair || d_cc, "d_col needs d_colpair or d_cc");
@@ -229,7 +238,7 @@ extern "C" int psl_feat_scatter(const int32_t* I, int64_t m, int64_t n_points, c
     unsigned* v_out = reinterpret_cast<unsigned*>(w); w += al256(sizeof(unsigned) * np);
     size_t cub_bytes = ws_bytes - (size_t)(w - static_cast<unsigned char*>(ws));
     TimingScope ts(T_SCATTER, st, 6);   // key kernel + 4 radix-sort passes + segment kernel
-    k_pair_keys<<<nblk(np, 256), 256, 0, st>>>(I, wn, np, (unsigned)n_points, k_in, v_in);
+    k_pair_keys<<<nblk(np, 256), 256, 0, st>>>(I, wn, np, (unsigned)n_points, row_map, k_in, v_in);
     int bits = 1;
     while ((1ll << bits) <= n_points) ++bits;
     PSL_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, k_in, k_out, v_in, v_out, (int)np, 0, bits, st));

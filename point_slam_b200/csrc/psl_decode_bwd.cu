@@ -900,9 +900,16 @@ struct ReduceJobs { ReduceJob j[64]; int n; };
 __global__ void k_reduce_partials(const float* __restrict__ partial, int n_cta, ReduceJobs jobs) {
     const ReduceJob J = jobs.j[blockIdx.y];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < J.n; e += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * GR_TOTAL + J.off + e];
-        J.dst[e] = s;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // 4 interleaved accumulators, combined in a fixed order
+        int c = 0;
+        for (; c + 4 <= n_cta; c += 4) {
+            s0 += partial[(size_t)c * GR_TOTAL + J.off + e];
+            s1 += partial[(size_t)(c + 1) * GR_TOTAL + J.off + e];
+            s2 += partial[(size_t)(c + 2) * GR_TOTAL + J.off + e];
+            s3 += partial[(size_t)(c + 3) * GR_TOTAL + J.off + e];
+        }
+        for (; c < n_cta; ++c) s0 += partial[(size_t)c * GR_TOTAL + J.off + e];
+        J.dst[e] = (s0 + s1) + (s2 + s3);
     }
 }
 

@@ -395,12 +395,21 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
 // ---------------------------------------------------------------------------------------------------------------------
 // fixed-order reduction of the per-CTA partials + combination into the reference-layout gradients
 // ---------------------------------------------------------------------------------------------------------------------
+// one thread per element; four interleaved accumulators (CTA c goes to accumulator c % 4) keep 4 loads in flight and are
+// combined in a fixed order, so the result does not depend on the launch configuration
 __global__ void k_wgrad_reduce(const float* __restrict__ partial, int n_cta, float* __restrict__ sums) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W_TOTAL; e += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * W_TOTAL + e];
-        sums[e] = s;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W_TOTAL) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        s0 += partial[(size_t)c * W_TOTAL + e];
+        s1 += partial[(size_t)(c + 1) * W_TOTAL + e];
+        s2 += partial[(size_t)(c + 2) * W_TOTAL + e];
+        s3 += partial[(size_t)(c + 3) * W_TOTAL + e];
     }
+    for (; c < n_cta; ++c) s0 += partial[(size_t)c * W_TOTAL + e];
+    sums[e] = (s0 + s1) + (s2 + s3);
 }
 
 struct FinArgs {
@@ -511,7 +520,7 @@ extern "C" int psl_wgrad_tc(const psl_decode_cfg* cfg, const psl_decoder_params*
         PSL_CHECK_CUDA(cudaGetLastError());
     }
     TimingScope ts(T_REDUCE, st, 2);
-    wgt::k_wgrad_reduce<<<64, 256, 0, st>>>(ws, (int)grid, sums);
+    wgt::k_wgrad_reduce<<<(wgt::W_TOTAL + 255) / 256, 256, 0, st>>>(ws, (int)grid, sums);
     wgt::FinArgs f{};
     f.P = *P; f.G = *G; f.sums = sums; f.rel = cfg->encode_rel_pos;
     const TBwd BL = tbwd_layout(m, cfg->encode_rel_pos);

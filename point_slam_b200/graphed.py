@@ -8,8 +8,12 @@ reference would have dropped (no depth, depth outlier) carry depth 0 and zero lo
 CUDA graph and replayed with a single launch.  Sums over the kept rays are identical to the reference's sums over the
 compacted rays; the dropped rays cost a few percent of extra render work.
 """
+import ctypes as C
+
 import torch
 
+from . import _lib as L
+from . import ops
 from .src import common
 
 
@@ -106,6 +110,114 @@ def mapper_iteration_static(renderer, npc, decoders, state, kfs, intr, n_pixels,
         loss = loss + w_color * _msum(torch.abs(b_color - color), m[:, None].expand(-1, 3))
     loss.backward()
     return loss.detach()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused shells: the same iterations with the glue (sampling, gate, loss + its gradient, pose chain rule, Adam on the pose /
+# the feature rows) done by the library's shell kernels (csrc/psl_shell.cu) and the render called without autograd.
+# One tracking iteration is ~17 kernel launches (was ~290), one colour-stage mapping iteration ~40 (was ~145).
+# ---------------------------------------------------------------------------------------------------------------------
+def _render_settings(renderer, npc, decoders, stage, is_tracker):
+    return decoders.settings(stage, renderer.N_surface, is_tracker, coef=renderer.sigmoid_coefficient,
+                             near_surface=renderer.near_end_surface, far_surface=renderer.far_end_surface,
+                             exposure_feat=None, radius_query=npc.get_radius_query())
+
+
+def _sample(lib, pix, K, per, H, W, H0, W0, ww, cam, c2w, color, depth, dyn, intr, device):
+    n = K * per
+    rays_o = torch.empty(n, 3, device=device); rays_d = torch.empty(n, 3, device=device)
+    b_depth = torch.empty(n, device=device); b_color = torch.empty(n, 3, device=device)
+    r2 = torch.empty(n, dtype=torch.float64, device=device) if dyn is not None else None
+    L.check(lib.psl_sample_rays(L.ptr(pix), K, per, H, W, H0, W0, ww, L.ptr(cam), L.ptr(c2w), L.ptr(color), L.ptr(depth),
+                                L.ptr(dyn), intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(rays_o), L.ptr(rays_d),
+                                L.ptr(b_depth), L.ptr(b_color), L.ptr(r2), L.stream()), 'psl_sample_rays')
+    depth_in = torch.empty(n, device=device)
+    inside = torch.empty(n, dtype=torch.uint8, device=device)
+    L.check(lib.psl_depth_gate(L.ptr(b_depth), n, L.ptr(depth_in), L.ptr(inside), L.stream()), 'psl_depth_gate')
+    return rays_o, rays_d, b_color, r2, depth_in, inside
+
+
+def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_depth, dyn_r_query, intr, n_pixels, device,
+                            geo_feats, col_feats, cloud_pos, edge, loss_out, w_color=0.5, pack=None, prepacked=False):
+    """tracker_iteration_static on the shell kernels.  cam (7) plain device tensor; writes d_cam (7) and loss_out ()."""
+    lib = L.load()
+    H, W = intr['H'], intr['W']
+    H0, W0, ww = edge[0], edge[1], W - 2 * edge[1]
+    n = n_pixels
+    pix = torch.randint((H - 2 * H0) * ww, (n,), device=device)
+    dyn = dyn_r_query if renderer.use_dynamic_radius else None
+    rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, 1, n, H, W, H0, W0, ww, cam, None, gt_color, gt_depth, dyn,
+                                                            intr, device)
+    st = _render_settings(renderer, npc, decoders, 'color', True)
+    rg, rc = decoders.draw_no_neighbor_vectors('color', device)
+    params = [ops._f32c(p) for p in decoders.kernel_params()]
+    depth, var, rgb, _, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg, rc,
+                                                cloud_pos, geo_feats, col_feats, None, True, colour_param_grads=False,
+                                                pack=pack, prepacked=prepacked)
+    d_depth = torch.empty(n, device=device); d_rgb = torch.empty(n, 3, device=device)
+    L.check(lib.psl_shell_loss(0, n, L.ptr(depth_in), L.ptr(inside), None, L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(b_color),
+                               w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
+    d_o, d_d, _, _, _, _ = ops.render_backward(sv, d_depth, None, d_rgb, True, True, False, False, False, [False] * L.N_PARAMS,
+                                               pack=pack, repack=False if prepacked else True)
+    L.check(lib.psl_pose_bwd(L.ptr(pix), n, H0, W0, ww, intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(cam), L.ptr(d_o),
+                             L.ptr(d_d), L.ptr(d_cam), L.stream()), 'psl_pose_bwd')
+
+
+class AdamRows:
+    """torch.optim.Adam state for `n_slots` rows of width `width` (psl_adam_rows)."""
+
+    def __init__(self, n_slots, width, device, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.n, self.w, self.lr, self.betas, self.eps = int(n_slots), int(width), float(lr), betas, float(eps)
+        self.grad = torch.zeros(n_slots, width, device=device)
+        self.m = torch.zeros(n_slots, width, device=device)
+        self.v = torch.zeros(n_slots, width, device=device)
+        self.t = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def reset(self):
+        self.grad.zero_(); self.m.zero_(); self.v.zero_(); self.t.zero_()
+
+    def step(self, param, rows=None, zero_grad=True):
+        L.check(L.load().psl_adam_rows(L.ptr(param), L.ptr(self.grad), L.ptr(self.m), L.ptr(self.v), L.ptr(rows), self.n, self.w,
+                                       L.ptr(self.t), self.lr, self.betas[0], self.betas[1], self.eps, int(zero_grad), L.stream()),
+                'psl_adam_rows')
+
+
+def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, device, stage, cloud_pos, loss_out, w_color=0.1,
+                           apply_adam=True):
+    """mapper_iteration_static on the shell kernels.  fs: FusedMapper state (full feature tensors updated in place by
+    AdamRows through the row list, compact gradients through row_map).  apply_adam=False leaves the gradients in
+    fs.adam_geo.grad / fs.adam_col.grad / fs.flat (tests)."""
+    lib = L.load()
+    H, W = intr['H'], intr['W']
+    K = kfs['depth'].shape[0]
+    per = n_pixels // K
+    n = K * per
+    color = stage == 'color'
+    pix = torch.randint(H * W, (K, per), device=device)
+    dyn = kfs['dyn_r_query'] if renderer.use_dynamic_radius else None
+    rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, K, per, H, W, 0, 0, W, None, kfs['c2w'], kfs['color'],
+                                                            kfs['depth'], dyn, intr, device)
+    st = _render_settings(renderer, npc, decoders, stage, False)
+    rg, rc = decoders.draw_no_neighbor_vectors(stage, device)
+    params = [ops._f32c(p) for p in decoders.kernel_params()]
+    depth, var, rgb, ray_mask, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg,
+                                                       rc if rc is not None else torch.zeros(32, device=device), cloud_pos,
+                                                       fs.npc_geo, fs.npc_col if color else None, None, True,
+                                                       colour_param_grads=color)
+    d_depth = torch.empty(n, device=device)
+    d_rgb = torch.empty(n, 3, device=device) if color else None
+    L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),
+                               L.ptr(b_color), w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
+    needs = fs.needs if color else [False] * L.N_PARAMS
+    ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, repack='bwd',
+                        flat_out=fs.flat if color else None,
+                        scatter_to=(fs.row_map, fs.u_max, fs.adam_geo.grad, fs.adam_col.grad))
+    if not apply_adam:
+        return
+    fs.adam_geo.step(fs.npc_geo, fs.rows)
+    if color:
+        fs.adam_col.step(fs.npc_col, fs.rows)
+        fs.dec_opt.step()
 
 
 def _reset_adam(opt):
@@ -255,14 +367,14 @@ class GraphedMapper:
     def run(self, stage, n_iters):
         done = 0
         if stage not in self.graphs:
-            if not self.warm:                              # one-time lazy initialisation outside of capture (executes once)
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    self._iter(stage)
-                torch.cuda.current_stream().wait_stream(s)
-                self.warm = True
-                done = 1
+            # lazy initialisation (optimizer state, kernel attributes, allocator) must happen OUTSIDE of the capture -- a
+            # state tensor created while capturing would be re-zeroed by every replay.  This executes one real iteration.
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._iter(stage)
+            torch.cuda.current_stream().wait_stream(s)
+            done = 1
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):                      # capture records the iteration, it does not execute it
                 self._iter(stage)
@@ -276,3 +388,167 @@ class GraphedMapper:
         st, U = self.state, self.n_used
         self.npc.update_geo_feats(st.geo.detach()[:U], st.indices[:U])
         self.npc.update_col_feats(st.col.detach()[:U], st.indices[:U])
+
+
+class FusedTracker:
+    """Tracker.optimize_cam_in_batch x n_iters: every iteration is one replay of a graph of ~17 library kernels
+    (tracker_iteration_fused).  The decoder is frozen while tracking, so its operand images are packed once per frame."""
+
+    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, edge=(20, 20), lr=0.002, w_color=0.5):
+        self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.edge, self.w = renderer, npc, decoders, intr, n_pixels, device, edge, w_color
+        H, W = intr['H'], intr['W']
+        self.color = torch.zeros(H, W, 3, device=device)
+        self.depth = torch.zeros(H, W, device=device)
+        self.dyn = torch.zeros(H, W, dtype=torch.float64, device=device)
+        self.cam = torch.zeros(7, device=device)
+        self.adam = AdamRows(1, 7, device, lr)
+        self.loss = torch.zeros((), device=device)
+        self.pack = ops.PackedDecoder(device)
+        self.graph = None
+        self.key = None
+
+    def _iter(self):
+        tracker_iteration_fused(self.r, self.npc, self.dec, self.cam, self.adam.grad, self.color, self.depth, self.dyn, self.intr,
+                                self.n, self.dev, self.npc.get_geo_feats(), self.npc.get_col_feats(), self.npc.cloud_pos_tensor(),
+                                self.edge, self.loss, self.w, pack=self.pack, prepacked=True)
+        self.adam.step(self.cam, None, zero_grad=False)
+
+    def load_frame(self, color, depth, dyn, cam_init):
+        self.color.copy_(color, non_blocking=True); self.depth.copy_(depth, non_blocking=True); self.dyn.copy_(dyn, non_blocking=True)
+        self.cam.copy_(cam_init)
+        self.adam.reset()
+        self.pack.pack(self.dec.kernel_params())           # the mapper may have updated the colour decoder since the last frame
+
+    def _graph_key(self):
+        return (self.npc.pts_num(), self.npc.spatial_hash().sorted_pts.data_ptr(), self.npc.get_geo_feats().data_ptr(),
+                self.npc.get_col_feats().data_ptr())
+
+    def capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        cam0 = self.cam.clone()
+        with torch.cuda.stream(s):
+            self._iter()                                   # lazy initialisation (caches, allocator) outside of the capture
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iter()
+        self.key = self._graph_key()
+        self.cam.copy_(cam0)
+        self.adam.reset()
+
+    def run(self, n_iters):
+        if self.graph is None or self.key != self._graph_key():    # the cloud changed (add_neural_points): re-capture
+            self.capture()
+        for _ in range(n_iters):
+            self.graph.replay()
+        return self.loss
+
+
+class FusedMapper:
+    """The joint loop of Mapper.optimize_map (Mapper.py:408-568) on the shell kernels, one graph replay per iteration.
+
+    Instead of the reference's slice tensors + index_put / gather round trip, the full feature tensors are optimised in place:
+    `rows` (u_max, padded with -1) lists the frustum-selected points, `row_map` is its inverse; the render backward scatters
+    feature gradients straight into compact (u_max,32) buffers and psl_adam_rows applies torch.optim.Adam's update to exactly
+    those rows.  The colour decoder keeps a torch fused Adam whose .grad tensors are views of one flat buffer that the
+    weight-gradient kernels write.  Graphs are captured once and survive new frusta; they are re-captured only when the
+    cloud (spatial hash / size) changes."""
+
+    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, w_color=0.1, lr_dec=0.005, lr_geo=0.005, lr_col=0.005,
+                 u_max=1 << 17):
+        self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.w = renderer, npc, decoders, intr, n_pixels, device, w_color
+        self.lrs = (lr_dec, lr_geo, lr_col)
+        self.loss = torch.zeros((), device=device)
+        self.u_max = int(u_max)
+        self.graphs = {}
+        self.key = None
+        self.warm = False
+        self.n_used = 0
+
+    def _alloc(self, N, n_kf):
+        H, W = self.intr['H'], self.intr['W']
+        d = self.dev
+        self.npc_geo = torch.zeros(N, 32, device=d)
+        self.npc_col = torch.zeros(N, 32, device=d)
+        self.rows = torch.full((self.u_max,), -1, dtype=torch.int64, device=d)
+        self.row_map = torch.full((N,), -1, dtype=torch.int32, device=d)
+        self.adam_geo = AdamRows(self.u_max, 32, d, self.lrs[1])
+        self.adam_col = AdamRows(self.u_max, 32, d, self.lrs[2])
+        plist = self.dec.kernel_params()
+        self.dec_params = [(nm, p) for nm, p in zip(ops.PARAM_ORDER, plist) if nm.startswith('c_') and p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for _, p in self.dec_params), device=d)
+        off = 0
+        for _, p in self.dec_params:
+            p.grad = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.dec_opt = torch.optim.Adam([p for _, p in self.dec_params], lr=self.lrs[0], capturable=True, fused=True)
+        self.dec_opt.step()                                # zero gradients: creates the state tensors OUTSIDE of any capture
+        _reset_adam(self.dec_opt)
+        self.keyframes = dict(color=torch.zeros(n_kf, H, W, 3, device=d), depth=torch.zeros(n_kf, H, W, device=d),
+                              c2w=torch.zeros(n_kf, 3, 4, device=d), dyn_r_query=torch.zeros(n_kf, H, W, dtype=torch.float64, device=d))
+        self.graphs = {}
+        self.warm = False
+
+    def begin_frame(self, indices, keyframes):
+        """indices: (U,) int64 rows of the feature tensors to optimise; keyframes: list of dicts (color, depth, c2w, dyn_r_query)."""
+        N, U = self.npc.pts_num(), int(indices.shape[0])
+        u_max = self.u_max
+        while U > u_max:
+            u_max *= 2
+        key = (N, u_max, len(keyframes), self.npc.spatial_hash().sorted_pts.data_ptr())
+        if key != self.key:
+            self.u_max = u_max
+            self._alloc(N, len(keyframes))
+            self.key = key
+        self.n_used = U
+        with torch.no_grad():
+            self.rows.fill_(-1)
+            self.rows[:U] = indices
+            self.row_map.fill_(-1)
+            self.row_map[indices] = torch.arange(U, dtype=torch.int32, device=self.dev)
+            self.npc_geo.copy_(self.npc.get_geo_feats())
+            self.npc_col.copy_(self.npc.get_col_feats())
+            for i, kf in enumerate(keyframes):
+                self.keyframes['color'][i].copy_(kf['color']); self.keyframes['depth'][i].copy_(kf['depth'])
+                self.keyframes['c2w'][i].copy_(kf['c2w'][:3, :4]); self.keyframes['dyn_r_query'][i].copy_(kf['dyn_r_query'])
+        self.adam_geo.reset(); self.adam_col.reset()
+        _reset_adam(self.dec_opt)
+        off = 0
+        for _, p in self.dec_params:                       # another optimizer's zero_grad(set_to_none) may have dropped the views
+            p.grad = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    @property
+    def needs(self):
+        want = {nm for nm, _ in self.dec_params}
+        return [nm in want for nm in ops.PARAM_ORDER]
+
+    def _iter(self, stage):
+        mapper_iteration_fused(self.r, self.npc, self.dec, self, self.keyframes, self.intr, self.n, self.dev, stage,
+                               self.npc.cloud_pos_tensor(), self.loss, self.w)
+
+    def run(self, stage, n_iters):
+        done = 0
+        if stage not in self.graphs:
+            # lazy initialisation (optimizer state, kernel attributes, allocator) must happen OUTSIDE of the capture -- a
+            # state tensor created while capturing would be re-zeroed by every replay.  This executes one real iteration.
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._iter(stage)
+            torch.cuda.current_stream().wait_stream(s)
+            done = 1
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                      # capture records the iteration, it does not execute it
+                self._iter(stage)
+            self.graphs[stage] = g
+        for _ in range(n_iters - done):
+            self.graphs[stage].replay()
+        return self.loss
+
+    def write_back(self):
+        """Optimised rows -> the neural point cloud (Mapper.py:605-610)."""
+        idx = self.rows[:self.n_used]
+        self.npc.update_geo_feats(self.npc_geo[idx], idx)
+        self.npc.update_col_feats(self.npc_col[idx], idx)

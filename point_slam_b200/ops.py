@@ -157,16 +157,6 @@ def surface_t_vals(S: int, device) -> torch.Tensor:
     return _T_VALS[key]
 
 
-_PACKED = {}
-
-
-def _packed_buffer(device):
-    key = str(device)
-    if key not in _PACKED:
-        _PACKED[key] = torch.empty(L.load().psl_packed_params_floats(), dtype=torch.float32, device=device)
-    return _PACKED[key]
-
-
 class RenderSettings:
     """Static (non-tensor) arguments of one render call."""
 
@@ -187,33 +177,51 @@ class RenderSettings:
 USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
-_TC_BWD_BLOB = {}
 
 
-def _tc_bwd_blob(device):
+class PackedDecoder:
+    """Device images of the decoder parameters in the kernels' operand layouts (FFMA blob, tcgen05 forward and backward
+    blobs).  The render calls re-pack into the per-device default instance on every call; a caller that knows the
+    parameters are frozen (tracking) packs ONCE into a private instance and passes it with prepacked=True."""
+
+    def __init__(self, device):
+        lib = L.load()
+        self.packed = torch.empty(lib.psl_packed_params_floats(), dtype=torch.float32, device=device)
+        self.blob = torch.empty(lib.psl_tc_blob_floats(), dtype=torch.float32, device=device)
+        self.bblob = torch.empty(lib.psl_tc_bwd_blob_floats(), dtype=torch.float32, device=device)
+
+    def pack(self, params, backward=True):
+        lib = L.load()
+        pstruct = _param_struct([_f32c(p.detach()) for p in params])
+        L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(self.packed), L.stream()), 'psl_pack_params')
+        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(self.blob), L.stream()), 'psl_tc_pack_params')
+        if backward:
+            L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(self.blob), lib.psl_tc_fold_offset_floats(), L.ptr(self.bblob),
+                                               L.stream()), 'psl_tc_bwd_pack_params')
+        return self
+
+
+_DEFAULT_PACK = {}
+
+
+def _default_pack(device):
     key = str(device)
-    if key not in _TC_BWD_BLOB:
-        _TC_BWD_BLOB[key] = torch.empty(L.load().psl_tc_bwd_blob_floats(), dtype=torch.float32, device=device)
-    return _TC_BWD_BLOB[key]
-_TC_BLOB = {}
-
-
-def _tc_blob(device):
-    key = str(device)
-    if key not in _TC_BLOB:
-        _TC_BLOB[key] = torch.empty(L.load().psl_tc_blob_floats(), dtype=torch.float32, device=device)
-    return _TC_BLOB[key]
+    if key not in _DEFAULT_PACK:
+        _DEFAULT_PACK[key] = PackedDecoder(device)
+    return _DEFAULT_PACK[key]
 
 
 def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
-                    affine, need_grad, colour_param_grads=True):
+                    affine, need_grad, colour_param_grads=True, pack=None, prepacked=False):
     """-> raw, has_nb, save (FFMA layout or None), tsave (tensor-core layout or None), param struct"""
     lib = L.load()
     dev = pos.device
     M = pos.shape[0]
-    packed = _packed_buffer(dev)
+    pk = pack if pack is not None else _default_pack(dev)
+    packed = pk.packed
     pstruct = _param_struct(params)
-    L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
+    if not prepacked:
+        L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
     save = tsave = None
@@ -234,8 +242,9 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                    L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
                                    L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd[geometry]')
-        blob = _tc_blob(dev)
-        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        blob = pk.blob
+        if not prepacked:
+            L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
         L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                      L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
                                      None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
@@ -247,8 +256,14 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
 
 
 def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, cloud_pos, geo, col, affine, raw, save,
-                     d_raw, want_pos, want_geo, want_col, want_affine, tsave=None):
-    """-> (d_pos, d_geo, d_col, param grads list, d_affine)"""
+                     d_raw, want_pos, want_geo, want_col, want_affine, tsave=None, pack=None, repack=True, flat_out=None,
+                     scatter_to=None):
+    """-> (d_pos, d_geo, d_col, param grads list, d_affine)
+    pack / repack: operand images to use and whether to rebuild them from `params`: True = forward and backward images,
+    'bwd' = backward image only (the forward of the same parameters has just packed the rest), False = the caller packed;
+    flat_out: caller-owned flat buffer for the requested parameter gradients (else allocated);
+    scatter_to = (row_map i32 (N), n_rows, d_geo (n_rows,32) or None, d_col (n_rows,32) or None): feature gradients go to these
+    PRE-ZEROED compact buffers (psl_feat_scatter_mapped) instead of fresh dense (N,32) tensors."""
     lib = L.load()
     dev = pos.device
     M = pos.shape[0]
@@ -264,7 +279,10 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
     # one flat buffer for all requested parameter gradients (k_reduce_partials writes every element: no memset needed)
     want = [bool(n and (color or name.startswith('g_')) and name != 'c_B') for n, name in zip(needs, L_PARAM_NAMES)]
     sizes = [p.numel() if w else 0 for p, w in zip(params, want)]
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev) if any(want) else None
+    flat = None
+    if any(want):
+        flat = flat_out if flat_out is not None else torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        assert flat.numel() == sum(sizes), 'flat_out does not match the requested parameter gradients'
     grads, off = [], 0
     for p, w, n_el in zip(params, want, sizes):
         grads.append(flat[off:off + n_el].view(p.shape) if w else None)
@@ -274,13 +292,16 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
     d_aff = torch.zeros(12, dtype=torch.float32, device=dev) if want_affine else None
     ws_bytes = lib.psl_decode_bwd_ws_bytes(M)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    packed = _packed_buffer(dev)
+    pk = pack if pack is not None else _default_pack(dev)
+    packed = pk.packed
     if tsave is not None:
         # colour branch on tensor cores (data gradients), then geometry branch + IDW weights + d_pos on the FFMA kernel
-        blob, bblob = _tc_blob(dev), _tc_bwd_blob(dev)
-        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
-        L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(blob), lib.psl_tc_fold_offset_floats(), L.ptr(bblob), L.stream()),
-                'psl_tc_bwd_pack_params')
+        blob, bblob = pk.blob, pk.bblob
+        if repack is True:
+            L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        if repack:
+            L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(blob), lib.psl_tc_fold_offset_floats(), L.ptr(bblob), L.stream()),
+                    'psl_tc_bwd_pack_params')
         tbwd = torch.empty(lib.psl_tc_bwd_tmp_floats(M, cfg.encode_rel_pos), dtype=torch.float32, device=dev)
         if wn is None:
             wn = torch.empty((M, 8), dtype=torch.float32, device=dev)
@@ -312,17 +333,93 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
                                    C.byref(gstruct), L.ptr(d_aff), None, None, L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
     d_geo = d_col = None
     if want_geo or want_col:
-        d_geo = torch.zeros_like(geo) if want_geo else None
-        d_col = torch.zeros_like(col) if want_col else None
         ws2_bytes = lib.psl_feat_scatter_ws_bytes(M)
         ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
-        L.check(lib.psl_feat_scatter(L.ptr(I), M, geo.shape[0], L.ptr(wn), L.ptr(d_cg),
-                                     L.ptr(d_colpair) if rel else None, None if rel else L.ptr(d_colpair),
-                                     L.ptr(d_geo), L.ptr(d_col), L.ptr(ws2), ws2_bytes, L.stream()), 'psl_feat_scatter')
+        if scatter_to is not None:
+            row_map, n_rows, d_geo, d_col = scatter_to
+            d_geo = d_geo if want_geo else None
+            d_col = d_col if want_col else None
+        else:
+            row_map, n_rows = None, geo.shape[0]
+            d_geo = torch.zeros_like(geo) if want_geo else None
+            d_col = torch.zeros_like(col) if want_col else None
+        L.check(lib.psl_feat_scatter_mapped(L.ptr(I), M, L.ptr(row_map), n_rows, L.ptr(wn), L.ptr(d_cg),
+                                            L.ptr(d_colpair) if rel else None, None if rel else L.ptr(d_colpair),
+                                            L.ptr(d_geo), L.ptr(d_col), L.ptr(ws2), ws2_bytes, L.stream()), 'psl_feat_scatter')
     return d_pos, d_geo, d_col, grads, d_aff
 
 
 L_PARAM_NAMES = PARAM_ORDER
+
+
+class RenderSaved:
+    """What render_backward needs from render_forward (plain attribute bag; the autograd node stores its tensors)."""
+    FIELDS = ('z_vals', 'pos', 'I', 'D', 'nn', 'r2_ray', 'cloud', 'geo', 'col', 'aff', 'raw', 'has_nb', 'save', 'tsave')
+
+    def __init__(self, st, cfg, tensors, params):
+        self.st, self.cfg, self.params = st, cfg, params
+        for k, v in zip(self.FIELDS, tensors):
+            setattr(self, k, v)
+
+    def tensors(self):
+        return tuple(getattr(self, k) for k in self.FIELDS)
+
+
+def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo, rand_col,
+                   cloud, geo, col, aff, need_grad, colour_param_grads=True, pack=None, prepacked=False):
+    """Ray-march + kNN -> decode -> composite on contiguous fp32 device tensors, without autograd.
+    -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) uint8, RenderSaved (activations only when need_grad)."""
+    lib = L.load()
+    dev = ro.device
+    R, S = ro.shape[0], st.S
+    M = R * S
+    z_vals = torch.empty((R, S), dtype=torch.float32, device=dev)
+    pos = torch.empty((M, 3), dtype=torch.float32, device=dev)
+    I = torch.empty((M, 8), dtype=torch.int32, device=dev)
+    D = torch.empty((M, 8), dtype=torch.float32, device=dev)
+    nn = torch.empty((M,), dtype=torch.int32, device=dev)
+    r2s = float(np.float32(st.radius_query ** 2))
+    L.check(lib.psl_raymarch_knn(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(gt_depth), R, S,
+                                 L.ptr(surface_t_vals(S, dev)), st.near_surface, st.far_surface, L.ptr(z_override),
+                                 L.ptr(r2_ray), r2s, L.ptr(z_vals), L.ptr(pos), L.ptr(I), L.ptr(D), L.ptr(nn),
+                                 L.stream()), 'psl_raymarch_knn')
+    cfg = st.cfg(S, r2s)
+    raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
+                                                  rand_col, aff, need_grad, colour_param_grads=colour_param_grads,
+                                                  pack=pack, prepacked=prepacked)
+    depth = torch.empty((R,), dtype=torch.float32, device=dev)
+    var = torch.empty((R,), dtype=torch.float32, device=dev)
+    rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(depth), L.ptr(var),
+                                  L.ptr(rgb), None, L.stream()), 'psl_composite_fwd')
+    ray_mask = torch.empty((R,), dtype=torch.uint8, device=dev)
+    L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
+    saved = RenderSaved(st, cfg, (z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave), params_c)
+    return depth, var, rgb, ray_mask, saved
+
+
+def render_backward(sv: RenderSaved, d_depth, d_var, d_rgb, want_o, want_d, want_geo, want_col, want_aff, needs,
+                    pack=None, repack=True, flat_out=None, scatter_to=None):
+    """Backward of render_forward.  d_* : contiguous fp32 gradients of depth / var / rgb (None = zero);
+    needs: per-parameter flags in PARAM_ORDER.  -> d_rays_o, d_rays_d, d_geo, d_col, d_affine, [param grads]"""
+    lib = L.load()
+    st = sv.st
+    R, S = sv.z_vals.shape
+    dev = sv.z_vals.device
+    d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
+    L.check(lib.psl_composite_bwd(L.ptr(sv.raw), L.ptr(sv.has_nb), L.ptr(sv.z_vals), R, S, st.coef, L.ptr(d_depth), L.ptr(d_var),
+                                  L.ptr(d_rgb), L.ptr(d_raw), L.stream()), 'psl_composite_bwd')
+    want_pos = want_o or want_d
+    d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, sv.cfg, sv.params, needs, sv.pos, sv.I, sv.D, sv.nn, sv.r2_ray,
+                                                         sv.cloud, sv.geo, sv.col, sv.aff, sv.raw, sv.save, d_raw, want_pos,
+                                                         want_geo, want_col, want_aff, tsave=sv.tsave, pack=pack, repack=repack,
+                                                         flat_out=flat_out, scatter_to=scatter_to)
+    d_o = d_d = None
+    if want_pos:
+        d_o = torch.empty((R, 3), dtype=torch.float32, device=dev) if want_o else None
+        d_d = torch.empty((R, 3), dtype=torch.float32, device=dev) if want_d else None
+        L.check(lib.psl_rays_bwd(L.ptr(d_pos), L.ptr(sv.z_vals), R, S, L.ptr(d_o), L.ptr(d_d), L.stream()), 'psl_rays_bwd')
+    return d_o, d_d, d_geo, d_col, (d_aff if want_aff else None), grads
 
 
 class _RenderFn(torch.autograd.Function):
@@ -331,71 +428,33 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, st: RenderSettings, grid: SpatialHash, gt_depth, z_override, r2_ray, rand_geo, rand_col,
                 cloud_pos, rays_o, rays_d, geo_feats, col_feats, affine, *params):
-        lib = L.load()
-        dev = rays_o.device
-        R, S = rays_o.shape[0], st.S
-        M = R * S
         ro, rd = _f32c(rays_o), _f32c(rays_d)
         geo = _f32c(geo_feats)
         col = _f32c(col_feats) if col_feats is not None else None
         cloud = _f32c(cloud_pos)
         params_c = [_f32c(p) for p in params]
         aff = _f32c(affine).reshape(-1) if affine is not None else None
-        z_vals = torch.empty((R, S), dtype=torch.float32, device=dev)
-        pos = torch.empty((M, 3), dtype=torch.float32, device=dev)
-        I = torch.empty((M, 8), dtype=torch.int32, device=dev)
-        D = torch.empty((M, 8), dtype=torch.float32, device=dev)
-        nn = torch.empty((M,), dtype=torch.int32, device=dev)
-        r2s = float(np.float32(st.radius_query ** 2))
-        L.check(lib.psl_raymarch_knn(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(gt_depth), R, S,
-                                     L.ptr(surface_t_vals(S, dev)), st.near_surface, st.far_surface, L.ptr(z_override),
-                                     L.ptr(r2_ray), r2s, L.ptr(z_vals), L.ptr(pos), L.ptr(I), L.ptr(D), L.ptr(nn),
-                                     L.stream()), 'psl_raymarch_knn')
-        cfg = st.cfg(S, r2s)
-        need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
         nig = ctx.needs_input_grad
+        need_grad = st.grad_mode and any(nig)     # grad mode is sampled by the caller: it is off inside forward()
         cpg = any(n and name.startswith('c_') for n, name in zip(nig[13:], L_PARAM_NAMES)) or bool(nig[12])
-        raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
-                                                      rand_col, aff, need_grad, colour_param_grads=cpg)
-        depth = torch.empty((R,), dtype=torch.float32, device=dev)
-        var = torch.empty((R,), dtype=torch.float32, device=dev)
-        rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
-        L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(depth), L.ptr(var),
-                                      L.ptr(rgb), None, L.stream()), 'psl_composite_fwd')
-        ray_mask = torch.empty((R,), dtype=torch.uint8, device=dev)
-        L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
-        ctx.st, ctx.cfg, ctx.n_params = st, cfg, len(params)
-        ctx.save_for_backward(z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave, *params_c)
+        depth, var, rgb, ray_mask, sv = render_forward(st, grid, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo,
+                                                       rand_col, cloud, geo, col, aff, need_grad, colour_param_grads=cpg)
+        ctx.st, ctx.cfg = st, sv.cfg
+        ctx.save_for_backward(*sv.tensors(), *params_c)
         ctx.mark_non_differentiable(ray_mask)
         return depth, var, rgb, ray_mask.bool()
 
     @staticmethod
     def backward(ctx, d_depth, d_var, d_rgb, _d_mask):
-        lib = L.load()
-        st, cfg = ctx.st, ctx.cfg
-        z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave = ctx.saved_tensors[:14]
-        params = list(ctx.saved_tensors[14:])
-        R, S = z_vals.shape
-        dev = z_vals.device
-        d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
+        n = len(RenderSaved.FIELDS)
+        sv = RenderSaved(ctx.st, ctx.cfg, ctx.saved_tensors[:n], list(ctx.saved_tensors[n:]))
         dd = _f32c(d_depth) if d_depth is not None else None
         dv = _f32c(d_var) if d_var is not None else None
         dc = _f32c(d_rgb) if d_rgb is not None else None
-        L.check(lib.psl_composite_bwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(dd), L.ptr(dv),
-                                      L.ptr(dc), L.ptr(d_raw), L.stream()), 'psl_composite_bwd')
         nig = ctx.needs_input_grad            # (st, grid, gt_depth, z_override, r2, rand_geo, rand_col, cloud, o, d, geo, col, affine, *params)
-        want_pos = nig[8] or nig[9]
-        needs = list(nig[13:])
-        d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, cfg, params, needs, pos, I, D, nn, r2_ray, cloud, geo,
-                                                             col, aff, raw, save, d_raw, want_pos, nig[10], nig[11], nig[12],
-                                                             tsave=tsave)
-        d_o = d_d = None
-        if want_pos:
-            d_o = torch.empty((R, 3), dtype=torch.float32, device=dev) if nig[8] else None
-            d_d = torch.empty((R, 3), dtype=torch.float32, device=dev) if nig[9] else None
-            L.check(lib.psl_rays_bwd(L.ptr(d_pos), L.ptr(z_vals), R, S, L.ptr(d_o), L.ptr(d_d), L.stream()), 'psl_rays_bwd')
-        return (None, None, None, None, None, None, None, None, d_o, d_d, d_geo, d_col,
-                d_aff if nig[12] else None, *grads)
+        d_o, d_d, d_geo, d_col, d_aff, grads = render_backward(sv, dd, dv, dc, nig[8], nig[9], nig[10], nig[11], nig[12],
+                                                               list(nig[13:]))
+        return (None, None, None, None, None, None, None, None, d_o, d_d, d_geo, d_col, d_aff, *grads)
 
 
 class _DecodeFn(torch.autograd.Function):

@@ -1,0 +1,315 @@
+"""The iteration-shell kernels (csrc/psl_shell.cu) and the fused shells built on them (point_slam_b200/graphed.py) against
+their torch restatements: the reference's own op sequences from src/common.py / Tracker.py / Mapper.py as restated in
+point_slam_b200/src/common.py and graphed.*_iteration_static (which tests/test_gpu_graphed.py ties to the reference-style
+shells).  Tolerances: sampled values exact; gradients / losses 1e-5 relative (fp32 reduction order differs)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _lib():
+    from point_slam_b200 import _lib as L
+    return L, L.load()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_sample_rays_matches_torch_ops():
+    from point_slam_b200.src import common
+    from point_slam_b200 import synth
+    L, lib = _lib()
+    intr = synth.TUM_INTRINSICS
+    H, W = intr['H'], intr['W']
+    g = torch.Generator(device=DEV).manual_seed(3)
+    color = torch.rand(H, W, 3, device=DEV, generator=g)
+    depth = torch.rand(H, W, device=DEV, generator=g) * 3
+    dyn = torch.rand(H, W, device=DEV, generator=g).double() * 0.1 + 0.02
+    cam = torch.tensor([0.9, 0.1, -0.3, 0.2, 0.5, -1.0, 2.0], device=DEV)         # un-normalised quaternion on purpose
+    e0, e1, n = 20, 30, 4096
+    ww = W - 2 * e1
+    pix = torch.randint((H - 2 * e0) * ww, (n,), device=DEV, generator=g)
+    ro = torch.empty(n, 3, device=DEV); rd = torch.empty(n, 3, device=DEV); bd = torch.empty(n, device=DEV)
+    bc = torch.empty(n, 3, device=DEV); r2 = torch.empty(n, dtype=torch.float64, device=DEV)
+    L.check(lib.psl_sample_rays(L.ptr(pix), 1, n, H, W, e0, e1, ww, L.ptr(cam), None, L.ptr(color), L.ptr(depth), L.ptr(dyn),
+                                intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(ro), L.ptr(rd), L.ptr(bd), L.ptr(bc), L.ptr(r2),
+                                L.stream()), 'psl_sample_rays')
+    jj = torch.div(pix, ww, rounding_mode='floor') + e0
+    ii = pix - (jj - e0) * ww + e1
+    c2w = common.get_camera_from_tensor(cam)
+    ro_t, rd_t = common.get_rays_from_uv(ii.float(), jj.float(), c2w, intr['fx'], intr['fy'], intr['cx'], intr['cy'], DEV)
+    assert torch.equal(bd, depth[jj, ii]) and torch.equal(bc, color[jj, ii]) and torch.equal(r2, dyn[jj, ii] ** 2)
+    assert torch.equal(ro, ro_t.expand(n, 3))
+    assert torch.equal(rd, rd_t)                          # same operation order as ATen's CUDA kernels: bit-identical rays
+    # c2w mode, several frames
+    K, per = 3, 1000
+    c2ws = torch.stack([common.get_camera_from_tensor(cam + 0.1 * k) for k in range(K)])
+    colors = torch.rand(K, H, W, 3, device=DEV, generator=g); depths = torch.rand(K, H, W, device=DEV, generator=g)
+    pix = torch.randint(H * W, (K, per), device=DEV, generator=g)
+    n = K * per
+    ro = torch.empty(n, 3, device=DEV); rd = torch.empty(n, 3, device=DEV); bd = torch.empty(n, device=DEV); bc = torch.empty(n, 3, device=DEV)
+    L.check(lib.psl_sample_rays(L.ptr(pix), K, per, H, W, 0, 0, W, None, L.ptr(c2ws), L.ptr(colors), L.ptr(depths), None,
+                                intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(ro), L.ptr(rd), L.ptr(bd), L.ptr(bc), None,
+                                L.stream()), 'psl_sample_rays')
+    jj = torch.div(pix, W, rounding_mode='floor'); ii = pix - jj * W
+    kk = torch.arange(K, device=DEV)[:, None].expand(K, per)
+    assert torch.equal(bd, depths[kk, jj, ii].reshape(-1)) and torch.equal(bc, colors[kk, jj, ii].reshape(-1, 3))
+    for k in range(K):
+        o, d = common.get_rays_from_uv(ii[k].float(), jj[k].float(), c2ws[k], intr['fx'], intr['fy'], intr['cx'], intr['cy'], DEV)
+        assert torch.equal(ro[k * per:(k + 1) * per], o.expand(per, 3)) and torch.equal(rd[k * per:(k + 1) * per], d)
+
+
+@pytest.mark.parametrize('n,frac_zero', [(1500, 0.1), (5000, 0.3), (8192, 0.0), (7, 0.5), (64, 1.0)])
+def test_depth_gate_matches_masked_stats(n, frac_zero):
+    from point_slam_b200 import graphed as G
+    L, lib = _lib()
+    g = torch.Generator(device=DEV).manual_seed(n)
+    d = torch.rand(n, device=DEV, generator=g) * 4 + 0.2
+    d[torch.rand(n, device=DEV, generator=g) < 0.02] = 60.0                          # outliers beyond 10 x median
+    d[torch.rand(n, device=DEV, generator=g) < frac_zero] = 0.0
+    if frac_zero >= 1.0:
+        d.zero_()
+    depth_in = torch.empty(n, device=DEV); inside = torch.empty(n, dtype=torch.uint8, device=DEV)
+    L.check(lib.psl_depth_gate(L.ptr(d), n, L.ptr(depth_in), L.ptr(inside), L.stream()), 'psl_depth_gate')
+    valid = d > 0
+    ref = valid & (d <= G._masked_stats(d, valid))
+    assert torch.equal(inside.bool(), ref)
+    assert torch.equal(depth_in, torch.where(ref, d, torch.zeros_like(d)))
+    # against the reference's own formulation on the compacted rays (Tracker.py:142-143)
+    if bool(valid.any()):
+        c = d[valid]
+        assert torch.equal(inside.bool()[valid], c <= torch.minimum(10 * c.median(), 1.2 * torch.max(c)))
+
+
+def _loss_inputs(n, seed, nan_inside):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    depth_in = torch.rand(n, device=DEV, generator=g) * 3 + 0.3
+    inside = torch.rand(n, device=DEV, generator=g) < 0.85
+    depth_in = torch.where(inside, depth_in, torch.zeros_like(depth_in))
+    depth = depth_in + 0.05 * torch.randn(n, device=DEV, generator=g)
+    depth[5::301] += 30.0                                                            # outliers: beyond 10 x mean
+    depth[3::401] += 3000.0                                                          # beyond the 1e3 clamp (tracking)
+    var = torch.rand(n, device=DEV, generator=g) * 1e-3 + 1e-6
+    nan_at = torch.zeros(n, dtype=torch.bool, device=DEV); nan_at[::97] = True
+    if not nan_inside:
+        nan_at &= ~inside
+    depth[nan_at] = float('nan')
+    rgb = torch.rand(n, 3, device=DEV, generator=g)
+    b_color = torch.rand(n, 3, device=DEV, generator=g)
+    ray_mask = torch.rand(n, device=DEV, generator=g) < 0.9
+    return depth_in, inside, ray_mask, depth.requires_grad_(True), var, rgb.requires_grad_(True), b_color
+
+
+def _torch_loss(G, mode, color, depth_in, inside, ray_mask, depth, var, rgb, b_color, w):
+    if mode == 0:                                            # graphed.tracker_iteration_static
+        tmp = torch.abs(depth_in - depth) / torch.sqrt(var + 1e-10)
+        with torch.no_grad():
+            ok = inside & (~torch.isnan(depth)) & (~torch.isnan(var))
+            mean_tmp = G._msum(tmp, inside) / inside.sum().clamp_min(1)
+            mask = ok & (tmp < 10 * mean_tmp)
+        return G._msum(torch.clamp(tmp, min=0.0, max=1e3), mask) + w * G._msum(torch.abs(b_color - rgb), mask[:, None].expand(-1, 3))
+    m = inside & ray_mask & (~torch.isnan(depth))            # graphed.mapper_iteration_static
+    loss = G._msum(torch.abs(depth_in - depth), m)
+    if color:
+        loss = loss + w * G._msum(torch.abs(b_color - rgb), m[:, None].expand(-1, 3))
+    return loss
+
+
+@pytest.mark.parametrize('mode,color,nan_inside', [(0, True, False), (1, True, True), (1, False, True), (0, True, True)])
+def test_shell_loss_and_gradients_match_autograd(mode, color, nan_inside):
+    """nan_inside with the tracking loss: a NaN depth among the gated rays poisons the mean exactly as in the reference
+    (tmp.mean() over the batch, Tracker.py:171) -> every ray is masked, loss 0."""
+    from point_slam_b200 import graphed as G
+    n = 3000
+    w = 0.5 if mode == 0 else 0.1
+    depth_in, inside, ray_mask, depth, var, rgb, b_color = _loss_inputs(n, 11 + mode, nan_inside)
+    loss = _torch_loss(G, mode, color, depth_in, inside, ray_mask, depth, var, rgb, b_color, w)
+    loss.backward()
+    if mode == 0 and nan_inside:
+        assert float(loss) == 0.0
+    else:
+        assert float(loss) > 0.0
+    _check_loss(mode, color, n, depth_in, inside, ray_mask, depth, var, rgb, b_color, w, loss)
+
+
+def _check_loss(mode, color, n, depth_in, inside, ray_mask, depth, var, rgb, b_color, w, loss):
+    L, lib = _lib()
+    out = torch.zeros((), device=DEV); dd = torch.empty(n, device=DEV); dc = torch.empty(n, 3, device=DEV) if color else None
+    ins = inside.to(torch.uint8).contiguous(); rm = ray_mask.to(torch.uint8).contiguous()
+    L.check(lib.psl_shell_loss(mode, n, L.ptr(depth_in), L.ptr(ins), L.ptr(rm), L.ptr(depth.detach()), L.ptr(var), L.ptr(rgb.detach()),
+                               L.ptr(b_color), w, L.ptr(out), L.ptr(dd), L.ptr(dc), L.stream()), 'psl_shell_loss')
+    assert abs(float(out) - float(loss)) <= 1e-5 * abs(float(loss)), (float(out), float(loss))
+    gd = torch.nan_to_num(depth.grad, nan=0.0)               # autograd leaves NaN where the masked-out input was NaN
+    assert float((dd - gd).abs().max()) <= 1e-6 * float(gd.abs().max().clamp_min(1e-30))
+    if color:
+        assert torch.equal(dc, rgb.grad if rgb.grad is not None else torch.zeros_like(dc))
+
+
+def test_pose_bwd_matches_autograd():
+    from point_slam_b200.src import common
+    from point_slam_b200 import synth
+    L, lib = _lib()
+    intr = synth.TUM_INTRINSICS
+    H, W = intr['H'], intr['W']
+    g = torch.Generator(device=DEV).manual_seed(8)
+    cam = torch.tensor([0.8, -0.2, 0.4, 0.1, 0.3, 0.2, -0.7], device=DEV, requires_grad=True)
+    e0, e1, n = 100, 100, 1500
+    ww = W - 2 * e1
+    pix = torch.randint((H - 2 * e0) * ww, (n,), device=DEV, generator=g)
+    jj = torch.div(pix, ww, rounding_mode='floor') + e0
+    ii = pix - (jj - e0) * ww + e1
+    ro, rd = common.get_rays_from_uv(ii.float(), jj.float(), common.get_camera_from_tensor(cam), intr['fx'], intr['fy'], intr['cx'],
+                                     intr['cy'], DEV)
+    g_o = torch.randn(n, 3, device=DEV, generator=g); g_d = torch.randn(n, 3, device=DEV, generator=g)
+    ((ro.expand(n, 3) * g_o).sum() + (rd * g_d).sum()).backward()
+    d_cam = torch.empty(7, device=DEV)
+    L.check(lib.psl_pose_bwd(L.ptr(pix), n, e0, e1, ww, intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(cam.detach()), L.ptr(g_o),
+                             L.ptr(g_d), L.ptr(d_cam), L.stream()), 'psl_pose_bwd')
+    assert _rel(d_cam, cam.grad) < 1e-5, (d_cam, cam.grad)
+
+
+def test_adam_rows_matches_torch_adam():
+    from point_slam_b200 import graphed as G
+    g = torch.Generator(device=DEV).manual_seed(2)
+    N, U = 5000, 1200
+    full = torch.randn(N, 32, device=DEV, generator=g)
+    idx = torch.randperm(N, device=DEV, generator=g)[:U]
+    rows = torch.full((2048,), -1, dtype=torch.int64, device=DEV); rows[:U] = idx
+    ref = full[idx].clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.005)
+    ad = G.AdamRows(2048, 32, DEV, 0.005)
+    mine = full.clone()
+    for it in range(25):
+        gr = torch.randn(U, 32, device=DEV, generator=g) * (10.0 ** float(it % 5 - 3))
+        gr[::7] = 0.0
+        ref.grad = gr.clone()
+        opt.step()
+        ad.grad[:U] = gr
+        ad.step(mine, rows)
+        assert float(ad.grad.abs().max()) == 0.0             # consumed gradients are cleared
+    assert _rel(mine[idx], ref.detach()) < 2e-6
+    untouched = torch.ones(N, dtype=torch.bool, device=DEV); untouched[idx] = False
+    assert torch.equal(mine[untouched], full[untouched])
+    # dense single row (the pose)
+    cam = torch.randn(7, device=DEV, generator=g); ref = cam.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.002); ad = G.AdamRows(1, 7, DEV, 0.002)
+    for it in range(40):
+        gr = torch.randn(7, device=DEV, generator=g)
+        ref.grad = gr.clone(); opt.step()
+        ad.grad.copy_(gr.view(1, 7)); ad.step(cam, None, zero_grad=False)
+    assert _rel(cam, ref.detach()) < 2e-6
+
+
+def _scene():
+    import bench
+    return bench, bench.GpuScene(0, DEV, 200000, 1)
+
+
+def test_fused_tracker_iteration_matches_static_shell():
+    from point_slam_b200 import graphed as G, ops
+    bench, scene = _scene()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.01, scene.rng).to(DEV)
+    cam = cam0.clone().requires_grad_(True)
+    torch.manual_seed(5)
+    loss_s = G.tracker_iteration_static(ren, npc, dec, cam, cur['color'], cur['depth'], cur['dyn_r_query'], bench.INTR, 1500, DEV,
+                                        npc.get_geo_feats(), npc.get_col_feats(), npc.cloud_pos_tensor(), (100, 100))
+    torch.manual_seed(5)
+    d_cam = torch.zeros(1, 7, device=DEV); loss_f = torch.zeros((), device=DEV)
+    pack = ops.PackedDecoder(DEV).pack(dec.kernel_params())
+    G.tracker_iteration_fused(ren, npc, dec, cam0.clone(), d_cam, cur['color'], cur['depth'], cur['dyn_r_query'], bench.INTR, 1500, DEV,
+                              npc.get_geo_feats(), npc.get_col_feats(), npc.cloud_pos_tensor(), (100, 100), loss_f, pack=pack,
+                              prepacked=True)
+    assert abs(float(loss_f) - float(loss_s)) / abs(float(loss_s)) < 1e-5, (float(loss_f), float(loss_s))
+    assert _rel(d_cam.view(-1), cam.grad) < 1e-4, (d_cam, cam.grad)
+
+
+@pytest.mark.parametrize('stage', ['geometry', 'color'])
+def test_fused_mapper_iteration_matches_static_shell(stage):
+    from point_slam_b200 import graphed as G, iteration as IT
+    bench, scene = _scene()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
+    kfl = [cur] + scene.keyframes
+    # torch-shell reference: slices + index_put + autograd
+    gm = G.GraphedMapper(ren, npc, dec, bench.INTR, 5000, DEV)
+    gm.begin_frame(idx, kfl)
+    st = gm.state
+    st.optimizer.zero_grad(set_to_none=True)
+    torch.manual_seed(9)
+    loss_s = G.mapper_iteration_static(ren, npc, dec, st, gm.keyframes, bench.INTR, 5000, DEV, stage, npc.cloud_pos_tensor())
+    U = idx.shape[0]
+    g_geo = st.geo.grad[:U].clone()
+    g_col = st.col.grad[:U].clone() if stage == 'color' else None
+    g_dec = {n: p.grad.clone() for n, p in dec.color_decoder.named_parameters() if p.grad is not None}
+    for p in dec.parameters():
+        p.grad = None
+    # fused
+    fm = G.FusedMapper(ren, npc, dec, bench.INTR, 5000, DEV)
+    fm.begin_frame(idx, kfl)
+    torch.manual_seed(9)
+    G.mapper_iteration_fused(ren, npc, dec, fm, fm.keyframes, bench.INTR, 5000, DEV, stage, npc.cloud_pos_tensor(), fm.loss,
+                             apply_adam=False)
+    assert abs(float(fm.loss) - float(loss_s)) / abs(float(loss_s)) < 1e-5, (float(fm.loss), float(loss_s))
+    assert _rel(fm.adam_geo.grad[:U], g_geo) < 1e-5
+    assert float(fm.adam_geo.grad[U:].abs().max()) == 0.0
+    if stage == 'color':
+        assert _rel(fm.adam_col.grad[:U], g_col) < 1e-5
+        assert len(g_dec) > 0
+        for n, p in dec.color_decoder.named_parameters():
+            if n in g_dec:
+                assert _rel(p.grad, g_dec[n]) < 1e-4, n
+
+
+def test_fused_graphs_run_and_optimise():
+    from point_slam_b200 import graphed as G, iteration as IT
+    bench, scene = _scene()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    ft = G.FusedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.02, scene.rng).to(DEV)
+    ft.load_frame(cur['color'], cur['depth'], cur['dyn_r_query'], cam0)
+    l0 = float(ft.run(1))
+    l1 = float(ft.run(40))
+    assert np.isfinite(l0) and np.isfinite(l1), (l0, l1)      # (random-init decoder: the loss value itself says little)
+    assert int(ft.adam.t) == 41
+    # same trajectory as the torch-shell graphs (same RNG stream, same Adam): poses agree after 41 iterations
+    gt = G.GraphedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    gt.capture()
+    poses = []
+    for tr in (ft, gt):
+        tr.load_frame(cur['color'], cur['depth'], cur['dyn_r_query'], cam0)
+        torch.manual_seed(77)
+        tr.run(41)
+        poses.append(tr.cam.detach().clone())
+    assert float((poses[0] - cam0).abs().max()) > 1e-3
+    assert float((poses[0] - poses[1]).abs().max()) < 2e-3 * float((poses[1] - cam0).abs().max()) + 1e-5, poses
+    fm = G.FusedMapper(ren, npc, dec, bench.INTR, 5000, DEV)
+    idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
+    fm.begin_frame(idx, [cur] + scene.keyframes)
+    g0 = fm.npc_geo.clone(); c0 = fm.npc_col.clone()
+    w0 = [p.detach().clone() for p in dec.color_decoder.parameters()]
+    la = float(fm.run('geometry', 3))
+    lb = float(fm.run('geometry', 20))
+    assert torch.equal(fm.npc_col, c0)                       # colour features do not move in the geometry stage
+    lc = float(fm.run('color', 2))
+    ld = float(fm.run('color', 20))
+    assert all(np.isfinite(x) for x in (la, lb, lc, ld)) and lb < la and ld < lc, (la, lb, lc, ld)
+    assert int(fm.adam_geo.t) == 45 and int(fm.adam_col.t) == 22
+    moved = (fm.npc_geo - g0).abs().sum(1) > 0
+    sel = torch.zeros_like(moved); sel[idx] = True
+    assert bool(moved.any()) and not bool((moved & ~sel).any())          # only frustum rows are optimised
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(w0, dec.color_decoder.parameters()))
+    before = npc.get_geo_feats().clone()
+    fm.write_back()
+    assert not torch.equal(before, npc.get_geo_feats())
+    n_graphs = len(fm.graphs)
+    fm.begin_frame(idx[: idx.shape[0] // 2], [cur] + scene.keyframes)    # a different frustum re-uses the graphs
+    le = float(fm.run('color', 3))
+    assert np.isfinite(le) and len(fm.graphs) == n_graphs
