@@ -688,30 +688,48 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
             float* sIn = gWc + 5 * 1024;        // [32][LD] layer input (16 B aligned: offset is a multiple of 4)
             float* sEmb = sDH2;                 // [96][LD] Fourier embedding (sDH2 is free in this phase)
             static_assert((32 * 93 + 3 * 1024 + 32 * 125 + 5 * 1024) % 4 == 0, "alignment");
-            stage_rows(gW0, a.P.g_W[0], 32 * 93);
-            stage_rows(gW1, a.P.g_W[1], 1024);
-            stage_rows(gW2, a.P.g_W[2], 1024);
-            stage_rows(gW3, a.P.g_W[3], 32 * 125);
-            stage_rows(gW4, a.P.g_W[4], 1024);
-            for (int i = 0; i < 5; ++i) stage_rows(gWc + 1024 * i, a.P.g_Wc[i], 1024);
+            if (color || wg || tile == (long long)blockIdx.x) {   // geometry-only data-gradient launches keep the matrices resident
+                stage_rows(gW0, a.P.g_W[0], 32 * 93);
+                stage_rows(gW1, a.P.g_W[1], 1024);
+                stage_rows(gW2, a.P.g_W[2], 1024);
+                stage_rows(gW3, a.P.g_W[3], 32 * 125);
+                stage_rows(gW4, a.P.g_W[4], 1024);
+                for (int i = 0; i < 5; ++i) stage_rows(gWc + 1024 * i, a.P.g_Wc[i], 1024);
+            }
+            // ReLU masks of all five layers up front (one coalesced 128-byte row per sample and layer): the loads are in flight
+            // while the weights are staged instead of being waited for layer by layer
+            unsigned zmask[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                unsigned mk = 0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const float z = (m0 + s < M) ? f.save[SL.gz * M + ((long long)i * M + m0 + s) * 32 + lane] : 0.f;
+                    mk |= (z > 0.f ? 1u : 0u) << s;
+                }
+                zmask[i] = mk;
+            }
+            const bool need_de = wg || (a.d_pos != nullptr);   // embedding gradient: only for g_B or the sample position
             __syncthreads();
             // d occ -> dh4 = Wo^T d occ
             const float wo = __ldg(a.P.g_Wo + lane);
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 sDH[lane * LD + col0 + s] = wo * sDRaw[s * 4 + 3];
-                sC[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.cg * M + (m0 + s) * 32 + lane] : 0.f;
-                sIn[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.gh * M + (4ll * M + m0 + s) * 32 + lane] : 0.f;
+                if (wg) {                                // layer inputs / c_g are operands of the weight gradients only
+                    sC[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.cg * M + (m0 + s) * 32 + lane] : 0.f;
+                    sIn[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.gh * M + (4ll * M + m0 + s) * 32 + lane] : 0.f;
+                }
             }
-            // geometry embedding (recomputed) + its argument cosines are needed at the end: keep sin in sEmb
-            {
+            // geometry embedding (recomputed for dW0 / dW3) + the accumulator of its gradient
+            if (need_de) {
                 for (int s = 0; s < SPW; ++s) {
                     const float x = __fmul_rn(kTwoPi, sP[s * 4]), y = __fmul_rn(kTwoPi, sP[s * 4 + 1]), z = __fmul_rn(kTwoPi, sP[s * 4 + 2]);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const int j = lane + 32 * t;
                         float v = 0.f;
-                        if (j < PSL_GEO_EMB)
+                        if (wg && j < PSL_GEO_EMB)
                             v = sinf(fmaf(z, __ldg(a.P.g_B + 2 * 93 + j), fmaf(y, __ldg(a.P.g_B + 93 + j), x * __ldg(a.P.g_B + j))));
                         sEmb[j * LD + col0 + s] = v;
                         sDE[j * LD + col0 + s] = 0.f;
@@ -748,13 +766,14 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
                 }
                 __syncthreads();
                 // (c) dz = dh * relu'(z)
+                {
+                    const unsigned mk = i == 4 ? zmask[4] : i == 3 ? zmask[3] : i == 2 ? zmask[2] : i == 1 ? zmask[1] : zmask[0];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const float z = (m0 + s < M) ? f.save[SL.gz * M + ((long long)i * M + m0 + s) * 32 + lane] : 0.f;
-                    if (!(z > 0.f)) dh[lane * LD + col0 + s] = 0.f;
+                    for (int s = 0; s < 8; ++s)
+                        if (!((mk >> s) & 1u)) dh[lane * LD + col0 + s] = 0.f;
                 }
                 // (d) layer input
-                if (i >= 1) {
+                if (wg && i >= 1) {
 #pragma unroll
                     for (int s = 0; s < 8; ++s)
                         sIn[lane * LD + col0 + s] = (m0 + s < M) ? f.save[SL.gh * M + ((long long)(i - 1) * M + m0 + s) * 32 + lane] : 0.f;
@@ -769,7 +788,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
                     rowsum_acc(dh, 32, part + GR_gb + 32 * i);
                 }
                 // (f) d_in = W_i^T dz
-                if (i == 0 || i == 3) {
+                if (need_de && (i == 0 || i == 3)) {
                     float de[3][8];
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
@@ -794,7 +813,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_bwd(BwdArgs a, long lo
                 float* t = dh; dh = dhn; dhn = t;
             }
             // geometry embedding gradient: sin only.  d arg = de * cos(arg);  d pos += 2 pi B d arg;  d B[c][j] += 2 pi p_c d arg
-            {
+            if (need_de) {
                 float gB[3][3];
 #pragma unroll
                 for (int t = 0; t < 3; ++t) { gB[t][0] = 0.f; gB[t][1] = 0.f; gB[t][2] = 0.f; }

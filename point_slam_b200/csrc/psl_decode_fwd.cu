@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_fwd(DecodeArgs a, long
 
         // ---------------- P2: geometry trunk ----------------------------------------------------------------
         __syncthreads();
-        stage_weights(sW, a.packed + OFF_GEO, G_SIZE);
+        if (color || tile == (long long)blockIdx.x)      // geometry-only launches keep the geometry stage resident
+            stage_weights(sW, a.packed + OFF_GEO, G_SIZE);
         __syncthreads();
         {
             // Fourier embedding sin(2 pi p B), 93 channels (+3 zero rows) into sB

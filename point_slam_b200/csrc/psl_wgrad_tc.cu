@@ -17,7 +17,9 @@ namespace psl {
 namespace wgt {
 
 constexpr int NWORK = 256, NTHR = 288;          // warps 0-7 staging workers, warp 8 MMA issuer + TMEM allocator
-constexpr int KC = 32;                          // samples per staged chunk (4 k-steps)
+constexpr int KC = 16;                          // samples per staged chunk (2 k-steps)
+constexpr int NS = 3;                           // staging ring depth: workers stage chunk i+1, i+2 while the MMAs of chunk i run
+constexpr int UPT = 128 / KC;                   // work units (chunks) per 128-sample tile
 
 // ---- per-CTA partial layout (floats) ------------------------------------------------------------------------------------
 __host__ __device__ constexpr int W_S1(int l) { return l * 32768; }                       // [128][128]  (l >= 1)
@@ -35,15 +37,16 @@ constexpr int W_DB1 = W_N2T + 4096;                                   // [128]
 constexpr int W_DB2 = W_DB1 + 128;                                    // [32]
 constexpr int W_TOTAL = W_DB2 + 32;
 
-// ---- shared memory (bytes) -----------------------------------------------------------------------------------------------
-constexpr int SB_A0 = 0;                        // A operand 0: [128 rows x 32 k] hi | lo   (32 KB)
-constexpr int SB_A1 = 32768;                    // A operand 1                              (32 KB)
-constexpr int SB_B = 65536;                     // B operand: up to 208 rows x 32 k, hi | lo (53248 B)
-constexpr int SB_B2 = SB_B + 53248;             // second small B (neighbour df / dout): 32 rows x 32 k hi | lo (8 KB)
-constexpr int SB_POS = SB_B2 + 8192;            // [128][4] positions of the tile
+// ---- shared memory (bytes): NS stages of {A0, A1, B, B2} ----------------------------------------------------------------
+constexpr int ST_A0 = 0;                        // A operand 0: [128 rows x 16 k] hi | lo   (16 KB)
+constexpr int ST_A1 = 16384;                    // A operand 1                              (16 KB)
+constexpr int ST_B = 32768;                     // B operand: up to 208 rows x 16 k, hi | lo (26 KB)
+constexpr int ST_B2 = ST_B + 26624;             // second small B (neighbour df / dout): 32 rows x 16 k hi | lo (4 KB)
+constexpr int ST_BYTES = ST_B2 + 4096;          // 63488
+constexpr int SB_POS = NS * ST_BYTES;           // [128][4] positions of the current tile
 constexpr int SB_VEC = SB_POS + 2048;           // Bc [3][20] (64) | Brel [3][12] (48)
 constexpr int SB_BAR = SB_VEC + 512;
-constexpr int SB_TOTAL = SB_BAR + 64;
+constexpr int SB_TOTAL = SB_BAR + 128;
 
 struct Args {
     psl_decode_cfg cfg;
@@ -58,7 +61,7 @@ struct Args {
 __device__ __forceinline__ float sp_fast(float z) { return softplus100_fast(z); }
 __device__ __forceinline__ float spg_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-fminf(100.0f * z, 30.0f))); }
 
-// store 4 consecutive-k values of row `row` (k0 multiple of 4) into a canonical (R rows) hi|lo operand image
+// store 4 consecutive-k values of row `row` (k0 multiple of 4) into a canonical (R rows x KC) hi|lo operand image
 __device__ __forceinline__ void put4(float* base, int R, int row, int k0, float4 v) {
     float4 hi, lo;
     tc::split_tf32(v.x, hi.x, lo.x); tc::split_tf32(v.y, hi.y, lo.y); tc::split_tf32(v.z, hi.z, lo.z); tc::split_tf32(v.w, hi.w, lo.w);
@@ -66,48 +69,66 @@ __device__ __forceinline__ void put4(float* base, int R, int row, int k0, float4
     *reinterpret_cast<float4*>(base + o) = hi;
     *reinterpret_cast<float4*>(base + R * KC + o) = lo;
 }
+__device__ __forceinline__ float sum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
 
-// MODE 0: v = x      1: v = x * softplus'(z)      2: v = softplus(z) (x ignored)
+// 128 rows x KC samples of one [channel][128 samples] plane: thread (row = tid / 2, 8 samples = 2 float4).
+// MODE 0: v = x      2: v = softplus(z)
 template <int MODE>
-__device__ __forceinline__ float rows128(float* dstA, const float* __restrict__ X, const float* __restrict__ Z, int m0c, int tid) {
-    // 128 rows x 32 samples: thread (row = tid/2, 16 samples)
-    const int row = tid >> 1, k0 = (tid & 1) * 16;
-    float rs = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE != 2) v = *reinterpret_cast<const float4*>(X + row * 128 + m0c + k0 + 4 * q);
-        if (MODE != 0) {
-            const float4 z = *reinterpret_cast<const float4*>(Z + row * 128 + m0c + k0 + 4 * q);
-            if (MODE == 1) { v.x *= spg_fast(z.x); v.y *= spg_fast(z.y); v.z *= spg_fast(z.z); v.w *= spg_fast(z.w); }
-            else { v.x = sp_fast(z.x); v.y = sp_fast(z.y); v.z = sp_fast(z.z); v.w = sp_fast(z.w); }
-        }
-        rs += (v.x + v.y) + (v.z + v.w);
-        put4(dstA, 128, row, k0 + 4 * q, v);
+__device__ __forceinline__ float rows128(float* dstA, const float* __restrict__ X, int m0c, int tid) {
+    const int row = tid >> 1, k0 = (tid & 1) * 8;
+    const float4 x0 = *reinterpret_cast<const float4*>(X + row * 128 + m0c + k0);
+    const float4 x1 = *reinterpret_cast<const float4*>(X + row * 128 + m0c + k0 + 4);
+    float4 v0 = x0, v1 = x1;
+    if (MODE == 2) {
+        v0 = make_float4(sp_fast(x0.x), sp_fast(x0.y), sp_fast(x0.z), sp_fast(x0.w));
+        v1 = make_float4(sp_fast(x1.x), sp_fast(x1.y), sp_fast(x1.z), sp_fast(x1.w));
     }
+    put4(dstA, 128, row, k0, v0);
+    put4(dstA, 128, row, k0 + 4, v1);
+    float rs = sum4(v0) + sum4(v1);
     rs += __shfl_xor_sync(0xffffffffu, rs, 1);
     return rs;                                      // row sum over the chunk (both threads of a row hold it)
+}
+// A0 = (dh * softplus'(z))^T, A1 = dh^T from one pass over dh and z; returns the two row sums
+__device__ __forceinline__ void stage_dz_dh(float* dA0, float* dA1, const float* __restrict__ DH, const float* __restrict__ Z, int m0c,
+                                            int tid, float& db, float& dbc) {
+    const int row = tid >> 1, k0 = (tid & 1) * 8;
+    float sdz = 0.f, sdh = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float4 h = *reinterpret_cast<const float4*>(DH + row * 128 + m0c + k0 + 4 * q);
+        const float4 z = *reinterpret_cast<const float4*>(Z + row * 128 + m0c + k0 + 4 * q);
+        const float4 d = make_float4(h.x * spg_fast(z.x), h.y * spg_fast(z.y), h.z * spg_fast(z.z), h.w * spg_fast(z.w));
+        put4(dA0, 128, row, k0 + 4 * q, d);
+        put4(dA1, 128, row, k0 + 4 * q, h);
+        sdz += sum4(d); sdh += sum4(h);
+    }
+    sdz += __shfl_xor_sync(0xffffffffu, sdz, 1);
+    sdh += __shfl_xor_sync(0xffffffffu, sdh, 1);
+    db += sdz; dbc += sdh;
 }
 
 __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* sA0 = reinterpret_cast<float*>(smem + SB_A0);
-    float* sA1 = reinterpret_cast<float*>(smem + SB_A1);
-    float* sB = reinterpret_cast<float*>(smem + SB_B);
-    float* sB2 = reinterpret_cast<float*>(smem + SB_B2);
     float* sPos = reinterpret_cast<float*>(smem + SB_POS);
     float* sVec = reinterpret_cast<float*>(smem + SB_VEC);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SB_BAR);
-    uint64_t* staged = bars;            // workers -> MMA (count 256)
-    uint64_t* consumed = bars + 1;      // MMA -> workers (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* staged = bars;            // [NS] workers -> MMA (count 256)
+    uint64_t* consumed = bars + NS;     // [NS] MMA -> workers (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const bool rel = a.cfg.encode_rel_pos != 0;
     const TSave TL = tsave_layout(a.m, a.cfg.encode_rel_pos);
     const TBwd BL = tbwd_layout(a.m, a.cfg.encode_rel_pos);
     float* part = a.partial + (size_t)blockIdx.x * W_TOTAL;
+    // this CTA's contiguous range of work units (unit = one KC-sample chunk of one tile)
+    const long long n_units = n_tiles * UPT;
+    const long long u0 = (long long)blockIdx.x * n_units / gridDim.x, u1 = (long long)(blockIdx.x + 1) * n_units / gridDim.x;
 
-    if (tid == 0) { tc::mbar_init(staged, NWORK); tc::mbar_init(consumed, 1); tc::mbar_fence_init(); }
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { tc::mbar_init(staged + s, NWORK); tc::mbar_init(consumed + s, 1); }
+        tc::mbar_fence_init();
+    }
     if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     if (tid < 60) sVec[tid] = a.P.c_B[tid];
     if (tid < 30) sVec[64 + (tid / 10) * 12 + (tid % 10)] = a.P.c_Brel[tid];
@@ -115,13 +136,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t a0 = tc::smem_u32(sA0), a1 = tc::smem_u32(sA1), b0 = tc::smem_u32(sB), b2 = tc::smem_u32(sB2);
-    uint32_t ps = 0, pc = 0;            // phases (MMA thread uses ps, workers use pc)
-    bool outstanding = false;           // workers: a committed MMA group has not been waited for yet
+    const uint32_t smem0 = tc::smem_u32(smem);
+    unsigned it = 0;                    // staged items so far (workers and the MMA thread walk the same sequence)
+    long long cur_tile = -1;
 
     // one MMA group: D[dcol : dcol+N] (+)= A(abase) x B(rows from brow, R rows total)
     auto mma_group = [&](uint32_t abase, uint32_t bbase, int R, int brow, int N, uint32_t dcol, uint32_t first) {
         const uint32_t idesc = tc::make_idesc_tf32(128, N), lboA = 128u * 16u, lboB = (uint32_t)R * 16u;
+#pragma unroll
         for (int j = 0; j < KC / 8; ++j) {
             const uint64_t ah = tc::make_smem_desc(abase + j * 2 * lboA, lboA, 128);
             const uint64_t al = tc::make_smem_desc(abase + 128 * KC * 4 + j * 2 * lboA, lboA, 128);
@@ -133,13 +155,39 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
             tc::mma_tf32_ss(tmem + dcol, ah, bl, idesc, 1);
         }
     };
-    auto hand_over = [&]() {            // workers: operands staged
-        tc::fence_proxy_async();
-        tc::mbar_arrive(staged);
-        outstanding = true;
+    // workers: claim the next ring stage (wait until the MMAs of its previous use are done) / hand it to the MMA thread
+    auto acquire = [&]() -> unsigned char* {
+        const unsigned s = it % NS, n = it / NS;
+        if (n > 0) tc::mbar_wait(consumed + s, (n - 1) & 1);
+        return smem + s * ST_BYTES;
     };
-    auto wait_consumed = [&]() {        // workers: previous chunk's MMAs are done with the staging buffers
-        if (outstanding) { tc::mbar_wait(consumed, pc); pc ^= 1; outstanding = false; }
+    auto hand_over = [&]() {
+        tc::fence_proxy_async();
+        tc::mbar_arrive(staged + it % NS);
+        ++it;
+    };
+    // MMA thread: wait for the next staged item; returns the stage's shared-memory address
+    auto mma_wait = [&]() -> uint32_t {
+        const unsigned s = it % NS, n = it / NS;
+        tc::mbar_wait(staged + s, n & 1);
+        tc::fence_after_sync();
+        return smem0 + s * ST_BYTES;
+    };
+    auto mma_done = [&]() { tc::mma_commit(consumed + it % NS); ++it; };
+    // workers: every MMA issued so far has completed (commits complete in order)
+    auto wait_all = [&]() {
+        if (it > 0) { const unsigned l = it - 1; tc::mbar_wait(consumed + l % NS, (l / NS) & 1); }
+        tc::fence_after_sync();
+    };
+    auto load_pos = [&](long long tile) {             // workers: positions of `tile` -> sPos (used by the embeddings)
+        if (tile == cur_tile) return;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = tid; i < 128 * 3; i += NWORK) {
+            const long long m = tile * 128 + i / 3;
+            sPos[(i / 3) * 4 + i % 3] = m < a.m ? a.pos[m * 3 + i % 3] : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_tile = tile;
     };
     // drain TMEM columns [col, col+ncols) of this thread's lane into partial rows (row = channel), both halves of the warp group
     auto drain = [&](uint32_t col, int ncols, float* dst, int ld) {
@@ -157,90 +205,83 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
     for (int grp = 0; grp < 2; ++grp) {
         const int l_hi = grp == 0 ? 4 : 2, l_lo = grp == 0 ? 3 : 0;
         float db_acc[3] = {0.f, 0.f, 0.f}, dbc_acc[3] = {0.f, 0.f, 0.f};
-        bool first_tile = true;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
-            if (warp < 8) {
-                wait_consumed();                    // every worker has finished staging the previous chunk (it was consumed)
-                for (int i = tid; i < 128 * 3; i += NWORK) {
-                    const long long m = tile * 128 + i / 3;
-                    sPos[(i / 3) * 4 + i % 3] = m < a.m ? a.pos[m * 3 + i % 3] : 0.f;
-                }
-            }
-            if (warp < 8) asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (long long u = u0; u < u1; ++u) {
+            const long long tile = u / UPT;
+            const int m0c = (int)(u % UPT) * KC;
+            if (warp < 8) load_pos(tile);                  // layers 3 and 0 embed the sample position
             for (int l = l_hi, li = 0; l >= l_lo; --l, ++li) {
-                const uint32_t base = (uint32_t)(li == 0 ? 0 : (li == 1 ? (grp == 0 ? 192 : 192) : 384));
+                const uint32_t base = (uint32_t)(li == 0 ? 0 : (li == 1 ? 192 : 384));
                 const int ncol1 = l == 0 ? 48 : (l == 3 ? 208 : 160);
                 const uint32_t s3col = base + ncol1;
                 const int R = l == 0 ? 80 : 208;                 // B rows: l >= 1: [a 128 | c 32 | e 48], l == 0: [e 48 | c 32]
                 const int crow = l == 0 ? 48 : 128;
-                const float* dhT = a.tbwd + BL.dhT + ((long long)l * n_tiles + tile) * 16384;
-                const float* zT = a.tsave + TL.zT + ((long long)l * n_tiles + tile) * 16384;
-                const float* zpT = l >= 1 ? a.tsave + TL.zT + ((long long)(l - 1) * n_tiles + tile) * 16384 : nullptr;
-                const float* cT = a.tsave + TL.cT + tile * 4096;
-                for (int ch = 0; ch < 128 / KC; ++ch) {
-                    const int m0c = ch * KC;
-                    if (warp < 8) {
-                        wait_consumed();
-                        db_acc[li] += rows128<1>(sA0, dhT, zT, m0c, tid);          // A0 = dz_l^T
-                        dbc_acc[li] += rows128<0>(sA1, dhT, nullptr, m0c, tid);    // A1 = dh_l^T
-                        // ---- B rows -------------------------------------------------------------------------------------
-                        if (l >= 1) {
-                            // a_{l-1}^T: rows 0..127 (re-stage with the right R)
-                            const int row = tid >> 1, k0 = (tid & 1) * 16;
+                if (warp < 8) {
+                    const float* dhT = a.tbwd + BL.dhT + ((long long)l * n_tiles + tile) * 16384;
+                    const float* zT = a.tsave + TL.zT + ((long long)l * n_tiles + tile) * 16384;
+                    const float* cT = a.tsave + TL.cT + tile * 4096;
+                    unsigned char* st = acquire();
+                    float* sA0 = reinterpret_cast<float*>(st + ST_A0);
+                    float* sA1 = reinterpret_cast<float*>(st + ST_A1);
+                    float* sB = reinterpret_cast<float*>(st + ST_B);
+                    stage_dz_dh(sA0, sA1, dhT, zT, m0c, tid, db_acc[li], dbc_acc[li]);   // A0 = dz_l^T, A1 = dh_l^T
+                    if (l >= 1) {                                                          // B rows 0..127 = a_{l-1}^T
+                        const float* zpT = a.tsave + TL.zT + ((long long)(l - 1) * n_tiles + tile) * 16384;
+                        const int row = tid >> 1, k0 = (tid & 1) * 8;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 z = *reinterpret_cast<const float4*>(zpT + row * 128 + m0c + k0 + 4 * q);
-                                put4(sB, R, row, k0 + 4 * q, make_float4(sp_fast(z.x), sp_fast(z.y), sp_fast(z.z), sp_fast(z.w)));
-                            }
+                        for (int q = 0; q < 2; ++q) {
+                            const float4 z = *reinterpret_cast<const float4*>(zpT + row * 128 + m0c + k0 + 4 * q);
+                            put4(sB, R, row, k0 + 4 * q, make_float4(sp_fast(z.x), sp_fast(z.y), sp_fast(z.z), sp_fast(z.w)));
                         }
-                        {   // c^T: 32 rows x 8 float4 = 256 items
-                            const int row = tid >> 3, q = tid & 7;
-                            put4(sB, R, crow + row, 4 * q, *reinterpret_cast<const float4*>(cT + row * 128 + m0c + 4 * q));
-                        }
-                        if (l == 0 || l == 3) {
-                            // e^T: rows j (sin) and 20+j (cos), j < 20; rows 40..47 zero.  item = (j, sample): 640 items
-                            const int erow = l == 0 ? 0 : 160;
-                            for (int it = tid; it < 20 * KC; it += NWORK) {
-                                const int j = it / KC, k = it - j * KC;
-                                const float* p = sPos + (m0c + k) * 4;
-                                const float x = __fmul_rn(kTwoPi, p[0]), y = __fmul_rn(kTwoPi, p[1]), z = __fmul_rn(kTwoPi, p[2]);
-                                float sn, cs;
-                                sincosf(fmaf(z, sVec[40 + j], fmaf(y, sVec[20 + j], x * sVec[j])), &sn, &cs);
-                                float hi, lo;
-                                const uint32_t o1 = tc::canon_off_floats(erow + j, k, R), o2 = tc::canon_off_floats(erow + 20 + j, k, R);
-                                tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[R * KC + o1] = lo;
-                                tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[R * KC + o2] = lo;
-                            }
-                            for (int it = tid; it < 8 * KC; it += NWORK) {
-                                const uint32_t o = tc::canon_off_floats(erow + 40 + it / KC, it % KC, R);
-                                sB[o] = 0.f; sB[R * KC + o] = 0.f;
-                            }
-                        }
-                        hand_over();
-                    } else if (lane == 0) {
-                        tc::mbar_wait(staged, ps); ps ^= 1; tc::fence_after_sync();
-                        const uint32_t first = (first_tile && ch == 0) ? 0u : 1u;
-                        mma_group(a0, b0, R, 0, ncol1, base, first);               // [S1 | S2 | S4]  (l == 0: S4)
-                        mma_group(a1, b0, R, crow, 32, s3col, first);              // S3 = dh^T c
-                        tc::mma_commit(consumed);
                     }
+                    if (tid < 128) {                                                       // c^T: 32 rows x 4 float4
+                        const int row = tid >> 2, q = tid & 3;
+                        put4(sB, R, crow + row, 4 * q, *reinterpret_cast<const float4*>(cT + row * 128 + m0c + 4 * q));
+                    }
+                    if (l == 0 || l == 3) {
+                        // e^T: rows j (sin) and 20+j (cos), j < 20; rows 40..47 zero.  item = (j, sample): 320 items
+                        const int erow = l == 0 ? 0 : 160;
+                        for (int i = tid; i < 20 * KC; i += NWORK) {
+                            const int j = i / KC, k = i - j * KC;
+                            const float* p = sPos + (m0c + k) * 4;
+                            const float x = __fmul_rn(kTwoPi, p[0]), y = __fmul_rn(kTwoPi, p[1]), z = __fmul_rn(kTwoPi, p[2]);
+                            float sn, cs;
+                            sincosf(fmaf(z, sVec[40 + j], fmaf(y, sVec[20 + j], x * sVec[j])), &sn, &cs);
+                            float hi, lo;
+                            const uint32_t o1 = tc::canon_off_floats(erow + j, k, R), o2 = tc::canon_off_floats(erow + 20 + j, k, R);
+                            tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[R * KC + o1] = lo;
+                            tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[R * KC + o2] = lo;
+                        }
+                        if (tid < 8 * KC) {
+                            const uint32_t o = tc::canon_off_floats(erow + 40 + tid / KC, tid % KC, R);
+                            sB[o] = 0.f; sB[R * KC + o] = 0.f;
+                        }
+                    }
+                    hand_over();
+                } else if (lane == 0) {
+                    const uint32_t sb = mma_wait();
+                    const uint32_t first = (u == u0) ? 0u : 1u;
+                    mma_group(sb + ST_A0, sb + ST_B, R, 0, ncol1, base, first);            // [S1 | S2 | S4]  (l == 0: S4)
+                    mma_group(sb + ST_A1, sb + ST_B, R, crow, 32, s3col, first);           // S3 = dh^T c
+                    mma_done();
                 }
             }
         }
         // ---- drain this group's accumulators into the partial buffer ------------------------------------------------------
         if (warp < 8) {
-            wait_consumed();
-            tc::fence_after_sync();
+            wait_all();
+            const bool any = u1 > u0;
             for (int l = l_hi, li = 0; l >= l_lo; --l, ++li) {
                 const uint32_t base = (uint32_t)(li == 0 ? 0 : (li == 1 ? 192 : 384));
-                if (l >= 1) {
-                    drain(base, 128, part + W_S1(l), 128);
-                    drain(base + 128, 32, part + W_S2(l), 32);
-                    if (l == 3) drain(base + 160, 48, part + W_S4(l), 48);
-                    drain(base + (l == 3 ? 208 : 160), 32, part + W_S3(l), 32);
-                } else {
-                    drain(base, 48, part + W_S4(0), 48);
-                    drain(base + 48, 32, part + W_S3(0), 32);
+                if (any) {
+                    if (l >= 1) {
+                        drain(base, 128, part + W_S1(l), 128);
+                        drain(base + 128, 32, part + W_S2(l), 32);
+                        if (l == 3) drain(base + 160, 48, part + W_S4(l), 48);
+                        drain(base + (l == 3 ? 208 : 160), 32, part + W_S3(l), 32);
+                    } else {
+                        drain(base, 48, part + W_S4(0), 48);
+                        drain(base + 48, 32, part + W_S3(0), 32);
+                    }
                 }
                 if ((tid & 1) == 0) { part[W_DB(l) + (tid >> 1)] = db_acc[li]; part[W_DBC(l) + (tid >> 1)] = dbc_acc[li]; }
             }
@@ -253,76 +294,73 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
     // =========================================== output layer + neighbour MLP ===============================================
     {
         float dbo_acc = 0.f, db1_acc = 0.f, db2_acc = 0.f;
-        if (warp < 8) {                                 // A1 rows 32..127 stay zero for the c^T dout product
-            for (int i = tid; i < 2 * 128 * KC; i += NWORK) sA1[i] = 0.f;
+        if (warp < 8) {                                 // A1 rows 32..127 stay zero for the c^T dout product (every stage)
+            for (int s = 0; s < NS; ++s) {
+                float* sA1 = reinterpret_cast<float*>(smem + s * ST_BYTES + ST_A1);
+                for (int i = tid; i < 2 * 128 * KC; i += NWORK) sA1[i] = 0.f;
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        bool first_tile = true;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
-            const float* z4T = a.tsave + TL.zT + (4ll * n_tiles + tile) * 16384;
-            const float* cT = a.tsave + TL.cT + tile * 4096;
-            const float* doutT = a.tbwd + BL.doutT + tile * 2048;
-            for (int ch = 0; ch < 128 / KC; ++ch) {
-                const int m0c = ch * KC;
-                if (warp < 8) {
-                    wait_consumed();
-                    rows128<2>(sA0, nullptr, z4T, m0c, tid);                        // A0 = a_4^T
-                    {   const int row = tid >> 3, q = tid & 7;                      // A1 rows 0..31 = c^T
-                        put4(sA1, 128, row, 4 * q, *reinterpret_cast<const float4*>(cT + row * 128 + m0c + 4 * q)); }
-                    if (tid < 128) {                                                // B2 = dout^T (16 rows)
-                        const int row = tid >> 3, q = tid & 7;
-                        const float4 v = *reinterpret_cast<const float4*>(doutT + row * 128 + m0c + 4 * q);
-                        put4(sB2, 16, row, 4 * q, v);
-                        float s = (v.x + v.y) + (v.z + v.w);
-                        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-                        dbo_acc += s;                                               // threads with q == 0 keep row sums
-                    }
-                    hand_over();
-                } else if (lane == 0) {
-                    tc::mbar_wait(staged, ps); ps ^= 1; tc::fence_after_sync();
-                    const uint32_t first = (first_tile && ch == 0) ? 0u : 1u;
-                    mma_group(a0, b2, 16, 0, 16, 0, first);                         // U1 = a_4^T dout
-                    mma_group(a1, b2, 16, 0, 16, 16, first);                        // U2 = [c^T; 0] dout
-                    tc::mma_commit(consumed);
+        for (long long u = u0; u < u1; ++u) {
+            const long long tile = u / UPT;
+            const int m0c = (int)(u % UPT) * KC;
+            if (warp < 8) {
+                const float* z4T = a.tsave + TL.zT + (4ll * n_tiles + tile) * 16384;
+                const float* cT = a.tsave + TL.cT + tile * 4096;
+                const float* doutT = a.tbwd + BL.doutT + tile * 2048;
+                unsigned char* st = acquire();
+                float* sA0 = reinterpret_cast<float*>(st + ST_A0);
+                float* sA1 = reinterpret_cast<float*>(st + ST_A1);
+                float* sB2 = reinterpret_cast<float*>(st + ST_B2);
+                rows128<2>(sA0, z4T, m0c, tid);                                        // A0 = a_4^T
+                if (tid < 128) {                                                       // A1 rows 0..31 = c^T
+                    const int row = tid >> 2, q = tid & 3;
+                    put4(sA1, 128, row, 4 * q, *reinterpret_cast<const float4*>(cT + row * 128 + m0c + 4 * q));
                 }
+                if (tid < 64) {                                                        // B2 = dout^T (16 rows x 4 float4)
+                    const int row = tid >> 2, q = tid & 3;
+                    const float4 v = *reinterpret_cast<const float4*>(doutT + row * 128 + m0c + 4 * q);
+                    put4(sB2, 16, row, 4 * q, v);
+                    float s = sum4(v);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    dbo_acc += s;                                                      // threads with q == 0 keep row sums
+                }
+                hand_over();
+            } else if (lane == 0) {
+                const uint32_t sb = mma_wait();
+                const uint32_t first = (u == u0) ? 0u : 1u;
+                mma_group(sb + ST_A0, sb + ST_B2, 16, 0, 16, 0, first);                // U1 = a_4^T dout
+                mma_group(sb + ST_A1, sb + ST_B2, 16, 0, 16, 16, first);               // U2 = [c^T; 0] dout
+                mma_done();
             }
         }
         if (rel) {
-            first_tile = true;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
-                const float* dccT = a.tbwd + BL.dccT + tile * 4096;
-                if (warp < 8) {
-                    wait_consumed();
-                    for (int i = tid; i < 128 * 3; i += NWORK) {
-                        const long long m = tile * 128 + i / 3;
-                        sPos[(i / 3) * 4 + i % 3] = m < a.m ? a.pos[m * 3 + i % 3] : 0.f;
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
+            for (long long u = u0; u < u1; ++u) {
+                const long long tile = u / UPT;
+                const int m0c = (int)(u % UPT) * KC;
+                if (warp < 8) load_pos(tile);
                 for (int k = 0; k < 8; ++k) {
-                    const float* dz1T = a.tbwd + BL.dz1T + (tile * 8 + k) * 16384;
-                    const float* z1T = a.tsave + TL.z1T + (tile * 8 + k) * 16384;
-                    const float* wnT = a.tsave + TL.wnT + (tile * 8 + k) * 128;
-                    for (int ch = 0; ch < 128 / KC; ++ch) {
-                        const int m0c = ch * KC;
-                        if (warp < 8) {
-                            wait_consumed();
-                            db1_acc += rows128<0>(sA0, dz1T, nullptr, m0c, tid);       // A0 = dz1^T
-                            rows128<2>(sA1, nullptr, z1T, m0c, tid);                   // A1 = softplus(z1)^T
-                            {   // B (64 rows) = x_k^T : thread (sample s = tid % 32, part p = tid / 32)
-                                const int s = tid & 31, p = tid >> 5;
-                                const long long m = tile * 128 + m0c + s;
-                                int id = -1;
-                                if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];
+                    if (warp < 8) {
+                        const float* dccT = a.tbwd + BL.dccT + tile * 4096;
+                        const float* dz1T = a.tbwd + BL.dz1T + (tile * 8 + k) * 16384;
+                        const float* z1T = a.tsave + TL.z1T + (tile * 8 + k) * 16384;
+                        const float* wnT = a.tsave + TL.wnT + (tile * 8 + k) * 128;
+                        unsigned char* st = acquire();
+                        float* sA0 = reinterpret_cast<float*>(st + ST_A0);
+                        float* sA1 = reinterpret_cast<float*>(st + ST_A1);
+                        float* sB = reinterpret_cast<float*>(st + ST_B);
+                        float* sB2 = reinterpret_cast<float*>(st + ST_B2);
+                        db1_acc += rows128<0>(sA0, dz1T, m0c, tid);                    // A0 = dz1^T
+                        rows128<2>(sA1, z1T, m0c, tid);                                // A1 = softplus(z1)^T
+                        {   // B (64 rows x 16 samples) = x_k^T : thread (sample s = tid % 16, part p = tid / 16):
+                            // p < 8: feature float4 p (rows 20 + 4p ..), p < 10: sin/cos j = p (rows p, 10 + p), p >= 10: zero rows 52..63
+                            const int s = tid & 15, p = tid >> 4;
+                            const long long m = tile * 128 + m0c + s;
+                            int id = -1;
+                            if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];
+                            if (p < 8) {
                                 float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                float rx = 0.f, ry = 0.f, rz = 0.f;
-                                if (id >= 0) {
-                                    f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32) + p);
-                                    const float* pp = sPos + (m0c + s) * 4;
-                                    rx = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3), pp[0]));
-                                    ry = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 1), pp[1]));
-                                    rz = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 2), pp[2]));
-                                }
+                                if (id >= 0) f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32) + p);
                                 const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
@@ -331,59 +369,63 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                                     const uint32_t o = tc::canon_off_floats(20 + 4 * p + c, s, 64);
                                     sB[o] = hi; sB[64 * KC + o] = lo;
                                 }
-#pragma unroll
-                                for (int t = 0; t < 3; ++t) {
-                                    const int jj = p + 8 * t;                               // jj < 10: p in 0..7 -> {p, p+8}
-                                    if (jj < 10) {
-                                        float sn = 0.f, cs = 0.f;
-                                        if (id >= 0) sincosf(fmaf(rz, sVec[64 + 24 + jj], fmaf(ry, sVec[64 + 12 + jj], rx * sVec[64 + jj])), &sn, &cs);
-                                        float hi, lo;
-                                        const uint32_t o1 = tc::canon_off_floats(jj, s, 64), o2 = tc::canon_off_floats(10 + jj, s, 64);
-                                        tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[64 * KC + o1] = lo;
-                                        tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[64 * KC + o2] = lo;
-                                    }
+                            }
+                            if (p < 10) {
+                                float sn = 0.f, cs = 0.f;
+                                if (id >= 0) {
+                                    const float* pp = sPos + (m0c + s) * 4;
+                                    const float rx = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3), pp[0]));
+                                    const float ry = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 1), pp[1]));
+                                    const float rz = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 2), pp[2]));
+                                    sincosf(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
                                 }
-                                if (p < 3) {                                                // zero rows 52..63
+                                float hi, lo;
+                                const uint32_t o1 = tc::canon_off_floats(p, s, 64), o2 = tc::canon_off_floats(10 + p, s, 64);
+                                tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[64 * KC + o1] = lo;
+                                tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[64 * KC + o2] = lo;
+                            } else {
 #pragma unroll
-                                    for (int c = 0; c < 4; ++c) {
-                                        const uint32_t o = tc::canon_off_floats(52 + 4 * p + c, s, 64);
-                                        sB[o] = 0.f; sB[64 * KC + o] = 0.f;
-                                    }
+                                for (int c = 0; c < 2; ++c) {
+                                    const uint32_t o = tc::canon_off_floats(52 + 2 * (p - 10) + c, s, 64);
+                                    sB[o] = 0.f; sB[64 * KC + o] = 0.f;
                                 }
                             }
-                            {   // B2 (32 rows) = df_k^T = wn_k * dcc^T
-                                const int row = tid >> 3, q = tid & 7;
-                                const float4 d = *reinterpret_cast<const float4*>(dccT + row * 128 + m0c + 4 * q);
-                                const float4 w = *reinterpret_cast<const float4*>(wnT + m0c + 4 * q);
-                                const float4 v = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
-                                put4(sB2, 32, row, 4 * q, v);
-                                float sm = (v.x + v.y) + (v.z + v.w);
-                                sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2); sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-                                db2_acc += sm;
-                            }
-                            hand_over();
-                        } else if (lane == 0) {
-                            tc::mbar_wait(staged, ps); ps ^= 1; tc::fence_after_sync();
-                            const uint32_t first = (first_tile && k == 0 && ch == 0) ? 0u : 1u;
-                            mma_group(a0, b0, 64, 0, 64, 32, first);                    // dN1   = dz1^T x
-                            mma_group(a1, b2, 32, 0, 32, 96, first);                    // dN2^T = softplus(z1)^T df
-                            tc::mma_commit(consumed);
                         }
+                        if (tid < 128) {   // B2 (32 rows x 4 float4) = df_k^T = wn_k * dcc^T
+                            const int row = tid >> 2, q = tid & 3;
+                            const float4 d = *reinterpret_cast<const float4*>(dccT + row * 128 + m0c + 4 * q);
+                            const float4 w = *reinterpret_cast<const float4*>(wnT + m0c + 4 * q);
+                            const float4 v = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
+                            put4(sB2, 32, row, 4 * q, v);
+                            float sm = sum4(v);
+                            sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                            db2_acc += sm;
+                        }
+                        hand_over();
+                    } else if (lane == 0) {
+                        const uint32_t sb = mma_wait();
+                        const uint32_t first = (u == u0 && k == 0) ? 0u : 1u;
+                        mma_group(sb + ST_A0, sb + ST_B, 64, 0, 64, 32, first);            // dN1   = dz1^T x
+                        mma_group(sb + ST_A1, sb + ST_B2, 32, 0, 32, 96, first);           // dN2^T = softplus(z1)^T df
+                        mma_done();
                     }
                 }
             }
         }
         if (warp < 8) {
-            wait_consumed();
-            tc::fence_after_sync();
-            drain(0, 16, part + W_U1, 16);
-            drain(16, 16, part + W_U2, 16);
-            if (tid < 128 && (tid & 7) == 0) part[W_DBO + (tid >> 3)] = dbo_acc;
+            wait_all();
+            if (u1 > u0) {
+                drain(0, 16, part + W_U1, 16);
+                drain(16, 16, part + W_U2, 16);
+            }
+            if (tid < 64 && (tid & 3) == 0) part[W_DBO + (tid >> 2)] = dbo_acc;
             if (rel) {
-                drain(32, 64, part + W_N1, 64);
-                drain(96, 32, part + W_N2T, 32);
+                if (u1 > u0) {
+                    drain(32, 64, part + W_N1, 64);
+                    drain(96, 32, part + W_N2T, 32);
+                }
                 if ((tid & 1) == 0) part[W_DB1 + (tid >> 1)] = db1_acc;
-                if ((tid & 7) == 0) part[W_DB2 + (tid >> 3)] = db2_acc;
+                if (tid < 128 && (tid & 3) == 0) part[W_DB2 + (tid >> 2)] = db2_acc;
             }
             tc::fence_before_sync();
         }
@@ -487,8 +529,8 @@ __global__ void k_wgrad_finalize(FinArgs a) {
 using namespace psl;
 
 static long long wgrad_grid(long long m) {
-    const long long n_tiles = (m + 127) / 128;
-    return n_tiles < sm_count() ? n_tiles : sm_count();
+    const long long n_units = (m + 127) / 128 * wgt::UPT;
+    return n_units < sm_count() ? n_units : sm_count();
 }
 
 extern "C" size_t psl_wgrad_tc_ws_floats(int64_t m) { return (size_t)wgt::W_TOTAL * (size_t)(wgrad_grid(m) + 1) + 64; }
