@@ -108,6 +108,9 @@ __device__ __forceinline__ void stage_dz_dh(float* dA0, float* dA1, const float*
     db += sdz; dbc += sdh;
 }
 
+struct TrunkRegs { float4 h[2], z[2], zp[2], c; };
+struct NbrRegs { float4 dz[2], z1[2], f4, dcc, w4; float cx, cy, cz; int id; };
+
 __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sPos = reinterpret_cast<float*>(smem + SB_POS);
@@ -205,65 +208,96 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
     for (int grp = 0; grp < 2; ++grp) {
         const int l_hi = grp == 0 ? 4 : 2, l_lo = grp == 0 ? 3 : 0;
         float db_acc[3] = {0.f, 0.f, 0.f}, dbc_acc[3] = {0.f, 0.f, 0.f};
-        for (long long u = u0; u < u1; ++u) {
-            const long long tile = u / UPT;
-            const int m0c = (int)(u % UPT) * KC;
-            if (warp < 8) load_pos(tile);                  // layers 3 and 0 embed the sample position
-            for (int l = l_hi, li = 0; l >= l_lo; --l, ++li) {
+        const int n_l = l_hi - l_lo + 1;
+        const long long n_items = (u1 - u0) * n_l;
+        if (warp < 8) {
+            // global operands of item j (unit u0 + j / n_l, layer l_hi - j % n_l), fetched one item ahead of their use
+            TrunkRegs cur, nxt;
+            auto fetch = [&](long long j, TrunkRegs& r) {
+                const long long u = u0 + j / n_l;
+                const int l = l_hi - (int)(j % n_l);
+                const long long tile = u / UPT;
+                const int m0c = (int)(u % UPT) * KC;
+                const int row = tid >> 1, k0 = (tid & 1) * 8;
+                const float* dhT = a.tbwd + BL.dhT + ((long long)l * n_tiles + tile) * 16384 + row * 128 + m0c + k0;
+                const float* zT = a.tsave + TL.zT + ((long long)l * n_tiles + tile) * 16384 + row * 128 + m0c + k0;
+                r.h[0] = *reinterpret_cast<const float4*>(dhT); r.h[1] = *reinterpret_cast<const float4*>(dhT + 4);
+                r.z[0] = *reinterpret_cast<const float4*>(zT); r.z[1] = *reinterpret_cast<const float4*>(zT + 4);
+                if (l >= 1) {
+                    const float* zpT = a.tsave + TL.zT + ((long long)(l - 1) * n_tiles + tile) * 16384 + row * 128 + m0c + k0;
+                    r.zp[0] = *reinterpret_cast<const float4*>(zpT); r.zp[1] = *reinterpret_cast<const float4*>(zpT + 4);
+                }
+                if (tid < 128) r.c = *reinterpret_cast<const float4*>(a.tsave + TL.cT + tile * 4096 + (tid >> 2) * 128 + m0c + 4 * (tid & 3));
+            };
+            if (n_items > 0) fetch(0, cur);
+            for (long long j = 0; j < n_items; ++j) {
+                const long long u = u0 + j / n_l;
+                const int li = (int)(j % n_l), l = l_hi - li;
+                const long long tile = u / UPT;
+                const int m0c = (int)(u % UPT) * KC;
+                if (li == 0) load_pos(tile);                 // layers 3 and 0 embed the sample position
+                if (j + 1 < n_items) fetch(j + 1, nxt);
+                const int R = l == 0 ? 80 : 208;             // B rows: l >= 1: [a 128 | c 32 | e 48], l == 0: [e 48 | c 32]
+                const int crow = l == 0 ? 48 : 128;
+                unsigned char* st = acquire();
+                float* sA0 = reinterpret_cast<float*>(st + ST_A0);
+                float* sA1 = reinterpret_cast<float*>(st + ST_A1);
+                float* sB = reinterpret_cast<float*>(st + ST_B);
+                {
+                    const int row = tid >> 1, k0 = (tid & 1) * 8;
+                    float sdz = 0.f, sdh = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {                                          // A0 = dz_l^T, A1 = dh_l^T
+                        const float4 h = cur.h[q], z = cur.z[q];
+                        const float4 d = make_float4(h.x * spg_fast(z.x), h.y * spg_fast(z.y), h.z * spg_fast(z.z), h.w * spg_fast(z.w));
+                        put4(sA0, 128, row, k0 + 4 * q, d);
+                        put4(sA1, 128, row, k0 + 4 * q, h);
+                        sdz += sum4(d); sdh += sum4(h);
+                        if (l >= 1) {                                                      // B rows 0..127 = a_{l-1}^T
+                            const float4 zp = cur.zp[q];
+                            put4(sB, R, row, k0 + 4 * q, make_float4(sp_fast(zp.x), sp_fast(zp.y), sp_fast(zp.z), sp_fast(zp.w)));
+                        }
+                    }
+                    sdz += __shfl_xor_sync(0xffffffffu, sdz, 1);
+                    sdh += __shfl_xor_sync(0xffffffffu, sdh, 1);
+                    if (li == 0) { db_acc[0] += sdz; dbc_acc[0] += sdh; }
+                    else if (li == 1) { db_acc[1] += sdz; dbc_acc[1] += sdh; }
+                    else { db_acc[2] += sdz; dbc_acc[2] += sdh; }
+                }
+                if (tid < 128) put4(sB, R, crow + (tid >> 2), 4 * (tid & 3), cur.c);       // c^T: 32 rows x 4 float4
+                if (l == 0 || l == 3) {
+                    // e^T: rows j (sin) and 20+j (cos), j < 20; rows 40..47 zero.  item = (j, sample): 320 items
+                    const int erow = l == 0 ? 0 : 160;
+                    for (int i = tid; i < 20 * KC; i += NWORK) {
+                        const int jj = i / KC, k = i - jj * KC;
+                        const float* p = sPos + (m0c + k) * 4;
+                        const float x = __fmul_rn(kTwoPi, p[0]), y = __fmul_rn(kTwoPi, p[1]), z = __fmul_rn(kTwoPi, p[2]);
+                        float sn, cs;
+                        sincosf(fmaf(z, sVec[40 + jj], fmaf(y, sVec[20 + jj], x * sVec[jj])), &sn, &cs);
+                        float hi, lo;
+                        const uint32_t o1 = tc::canon_off_floats(erow + jj, k, R), o2 = tc::canon_off_floats(erow + 20 + jj, k, R);
+                        tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[R * KC + o1] = lo;
+                        tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[R * KC + o2] = lo;
+                    }
+                    if (tid < 8 * KC) {
+                        const uint32_t o = tc::canon_off_floats(erow + 40 + tid / KC, tid % KC, R);
+                        sB[o] = 0.f; sB[R * KC + o] = 0.f;
+                    }
+                }
+                hand_over();
+                cur = nxt;
+            }
+        } else if (lane == 0) {
+            for (long long j = 0; j < n_items; ++j) {
+                const int li = (int)(j % n_l), l = l_hi - li;
                 const uint32_t base = (uint32_t)(li == 0 ? 0 : (li == 1 ? 192 : 384));
                 const int ncol1 = l == 0 ? 48 : (l == 3 ? 208 : 160);
-                const uint32_t s3col = base + ncol1;
-                const int R = l == 0 ? 80 : 208;                 // B rows: l >= 1: [a 128 | c 32 | e 48], l == 0: [e 48 | c 32]
-                const int crow = l == 0 ? 48 : 128;
-                if (warp < 8) {
-                    const float* dhT = a.tbwd + BL.dhT + ((long long)l * n_tiles + tile) * 16384;
-                    const float* zT = a.tsave + TL.zT + ((long long)l * n_tiles + tile) * 16384;
-                    const float* cT = a.tsave + TL.cT + tile * 4096;
-                    unsigned char* st = acquire();
-                    float* sA0 = reinterpret_cast<float*>(st + ST_A0);
-                    float* sA1 = reinterpret_cast<float*>(st + ST_A1);
-                    float* sB = reinterpret_cast<float*>(st + ST_B);
-                    stage_dz_dh(sA0, sA1, dhT, zT, m0c, tid, db_acc[li], dbc_acc[li]);   // A0 = dz_l^T, A1 = dh_l^T
-                    if (l >= 1) {                                                          // B rows 0..127 = a_{l-1}^T
-                        const float* zpT = a.tsave + TL.zT + ((long long)(l - 1) * n_tiles + tile) * 16384;
-                        const int row = tid >> 1, k0 = (tid & 1) * 8;
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const float4 z = *reinterpret_cast<const float4*>(zpT + row * 128 + m0c + k0 + 4 * q);
-                            put4(sB, R, row, k0 + 4 * q, make_float4(sp_fast(z.x), sp_fast(z.y), sp_fast(z.z), sp_fast(z.w)));
-                        }
-                    }
-                    if (tid < 128) {                                                       // c^T: 32 rows x 4 float4
-                        const int row = tid >> 2, q = tid & 3;
-                        put4(sB, R, crow + row, 4 * q, *reinterpret_cast<const float4*>(cT + row * 128 + m0c + 4 * q));
-                    }
-                    if (l == 0 || l == 3) {
-                        // e^T: rows j (sin) and 20+j (cos), j < 20; rows 40..47 zero.  item = (j, sample): 320 items
-                        const int erow = l == 0 ? 0 : 160;
-                        for (int i = tid; i < 20 * KC; i += NWORK) {
-                            const int j = i / KC, k = i - j * KC;
-                            const float* p = sPos + (m0c + k) * 4;
-                            const float x = __fmul_rn(kTwoPi, p[0]), y = __fmul_rn(kTwoPi, p[1]), z = __fmul_rn(kTwoPi, p[2]);
-                            float sn, cs;
-                            sincosf(fmaf(z, sVec[40 + j], fmaf(y, sVec[20 + j], x * sVec[j])), &sn, &cs);
-                            float hi, lo;
-                            const uint32_t o1 = tc::canon_off_floats(erow + j, k, R), o2 = tc::canon_off_floats(erow + 20 + j, k, R);
-                            tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[R * KC + o1] = lo;
-                            tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[R * KC + o2] = lo;
-                        }
-                        if (tid < 8 * KC) {
-                            const uint32_t o = tc::canon_off_floats(erow + 40 + tid / KC, tid % KC, R);
-                            sB[o] = 0.f; sB[R * KC + o] = 0.f;
-                        }
-                    }
-                    hand_over();
-                } else if (lane == 0) {
-                    const uint32_t sb = mma_wait();
-                    const uint32_t first = (u == u0) ? 0u : 1u;
-                    mma_group(sb + ST_A0, sb + ST_B, R, 0, ncol1, base, first);            // [S1 | S2 | S4]  (l == 0: S4)
-                    mma_group(sb + ST_A1, sb + ST_B, R, crow, 32, s3col, first);           // S3 = dh^T c
-                    mma_done();
-                }
+                const int R = l == 0 ? 80 : 208, crow = l == 0 ? 48 : 128;
+                const uint32_t sb = mma_wait();
+                const uint32_t first = (j < n_l) ? 0u : 1u;
+                mma_group(sb + ST_A0, sb + ST_B, R, 0, ncol1, base, first);                // [S1 | S2 | S4]  (l == 0: S4)
+                mma_group(sb + ST_A1, sb + ST_B, R, crow, 32, base + ncol1, first);        // S3 = dh^T c
+                mma_done();
             }
         }
         // ---- drain this group's accumulators into the partial buffer ------------------------------------------------------
@@ -335,80 +369,115 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
             }
         }
         if (rel) {
-            for (long long u = u0; u < u1; ++u) {
-                const long long tile = u / UPT;
-                const int m0c = (int)(u % UPT) * KC;
-                if (warp < 8) load_pos(tile);
-                for (int k = 0; k < 8; ++k) {
-                    if (warp < 8) {
-                        const float* dccT = a.tbwd + BL.dccT + tile * 4096;
-                        const float* dz1T = a.tbwd + BL.dz1T + (tile * 8 + k) * 16384;
-                        const float* z1T = a.tsave + TL.z1T + (tile * 8 + k) * 16384;
-                        const float* wnT = a.tsave + TL.wnT + (tile * 8 + k) * 128;
-                        unsigned char* st = acquire();
-                        float* sA0 = reinterpret_cast<float*>(st + ST_A0);
-                        float* sA1 = reinterpret_cast<float*>(st + ST_A1);
-                        float* sB = reinterpret_cast<float*>(st + ST_B);
-                        float* sB2 = reinterpret_cast<float*>(st + ST_B2);
-                        db1_acc += rows128<0>(sA0, dz1T, m0c, tid);                    // A0 = dz1^T
-                        rows128<2>(sA1, z1T, m0c, tid);                                // A1 = softplus(z1)^T
-                        {   // B (64 rows x 16 samples) = x_k^T : thread (sample s = tid % 16, part p = tid / 16):
-                            // p < 8: feature float4 p (rows 20 + 4p ..), p < 10: sin/cos j = p (rows p, 10 + p), p >= 10: zero rows 52..63
-                            const int s = tid & 15, p = tid >> 4;
-                            const long long m = tile * 128 + m0c + s;
-                            int id = -1;
-                            if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];
-                            if (p < 8) {
-                                float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (id >= 0) f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32) + p);
-                                const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    float hi, lo;
-                                    tc::split_tf32(fv[c], hi, lo);
-                                    const uint32_t o = tc::canon_off_floats(20 + 4 * p + c, s, 64);
-                                    sB[o] = hi; sB[64 * KC + o] = lo;
-                                }
-                            }
-                            if (p < 10) {
-                                float sn = 0.f, cs = 0.f;
-                                if (id >= 0) {
-                                    const float* pp = sPos + (m0c + s) * 4;
-                                    const float rx = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3), pp[0]));
-                                    const float ry = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 1), pp[1]));
-                                    const float rz = __fmul_rn(kTwoPi, __fsub_rn(__ldg(a.cloud_pos + (size_t)id * 3 + 2), pp[2]));
-                                    sincosf(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
-                                }
-                                float hi, lo;
-                                const uint32_t o1 = tc::canon_off_floats(p, s, 64), o2 = tc::canon_off_floats(10 + p, s, 64);
-                                tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[64 * KC + o1] = lo;
-                                tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[64 * KC + o2] = lo;
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 2; ++c) {
-                                    const uint32_t o = tc::canon_off_floats(52 + 2 * (p - 10) + c, s, 64);
-                                    sB[o] = 0.f; sB[64 * KC + o] = 0.f;
-                                }
-                            }
-                        }
-                        if (tid < 128) {   // B2 (32 rows x 4 float4) = df_k^T = wn_k * dcc^T
-                            const int row = tid >> 2, q = tid & 3;
-                            const float4 d = *reinterpret_cast<const float4*>(dccT + row * 128 + m0c + 4 * q);
-                            const float4 w = *reinterpret_cast<const float4*>(wnT + m0c + 4 * q);
-                            const float4 v = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
-                            put4(sB2, 32, row, 4 * q, v);
-                            float sm = sum4(v);
-                            sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-                            db2_acc += sm;
-                        }
-                        hand_over();
-                    } else if (lane == 0) {
-                        const uint32_t sb = mma_wait();
-                        const uint32_t first = (u == u0 && k == 0) ? 0u : 1u;
-                        mma_group(sb + ST_A0, sb + ST_B, 64, 0, 64, 32, first);            // dN1   = dz1^T x
-                        mma_group(sb + ST_A1, sb + ST_B2, 32, 0, 32, 96, first);           // dN2^T = softplus(z1)^T df
-                        mma_done();
+            const long long n_items = (u1 - u0) * 8;
+            if (warp < 8) {
+                const int s = tid & 15, p = tid >> 4;
+                NbrRegs cur, nxt;
+                // global operands of item j (unit u0 + j / 8, neighbour j % 8), fetched one item ahead (the neighbour's feature row
+                // and position need its index first: that dependent chain is what the prefetch hides)
+                auto fetch = [&](long long j, NbrRegs& r) {
+                    const long long u = u0 + (j >> 3);
+                    const int k = (int)(j & 7);
+                    const long long tile = u / UPT;
+                    const int m0c = (int)(u % UPT) * KC;
+                    const int row = tid >> 1, k0 = (tid & 1) * 8;
+                    const float* dz1T = a.tbwd + BL.dz1T + (tile * 8 + k) * 16384 + row * 128 + m0c + k0;
+                    const float* z1T = a.tsave + TL.z1T + (tile * 8 + k) * 16384 + row * 128 + m0c + k0;
+                    const float* wnT = a.tsave + TL.wnT + (tile * 8 + k) * 128;
+                    r.dz[0] = *reinterpret_cast<const float4*>(dz1T); r.dz[1] = *reinterpret_cast<const float4*>(dz1T + 4);
+                    r.z1[0] = *reinterpret_cast<const float4*>(z1T); r.z1[1] = *reinterpret_cast<const float4*>(z1T + 4);
+                    const long long m = tile * 128 + m0c + s;
+                    int id = -1;
+                    if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];
+                    r.id = id;
+                    r.f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    r.cx = r.cy = r.cz = 0.f;
+                    if (id >= 0) {
+                        if (p < 8) r.f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32) + p);
+                        if (p < 10) { r.cx = __ldg(a.cloud_pos + (size_t)id * 3); r.cy = __ldg(a.cloud_pos + (size_t)id * 3 + 1); r.cz = __ldg(a.cloud_pos + (size_t)id * 3 + 2); }
                     }
+                    if (tid < 128) {
+                        r.dcc = *reinterpret_cast<const float4*>(a.tbwd + BL.dccT + tile * 4096 + (tid >> 2) * 128 + m0c + 4 * (tid & 3));
+                        r.w4 = *reinterpret_cast<const float4*>(wnT + m0c + 4 * (tid & 3));
+                    }
+                };
+                if (n_items > 0) fetch(0, cur);
+                for (long long j = 0; j < n_items; ++j) {
+                    const long long u = u0 + (j >> 3);
+                    const int k = (int)(j & 7);
+                    const long long tile = u / UPT;
+                    const int m0c = (int)(u % UPT) * KC;
+                    if (k == 0) load_pos(tile);
+                    if (j + 1 < n_items) fetch(j + 1, nxt);
+                    unsigned char* st = acquire();
+                    float* sA0 = reinterpret_cast<float*>(st + ST_A0);
+                    float* sA1 = reinterpret_cast<float*>(st + ST_A1);
+                    float* sB = reinterpret_cast<float*>(st + ST_B);
+                    float* sB2 = reinterpret_cast<float*>(st + ST_B2);
+                    {
+                        const int row = tid >> 1, k0 = (tid & 1) * 8;
+                        float rs = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            put4(sA0, 128, row, k0 + 4 * q, cur.dz[q]);                                    // A0 = dz1^T
+                            rs += sum4(cur.dz[q]);
+                            const float4 z = cur.z1[q];
+                            put4(sA1, 128, row, k0 + 4 * q, make_float4(sp_fast(z.x), sp_fast(z.y), sp_fast(z.z), sp_fast(z.w)));   // A1 = softplus(z1)^T
+                        }
+                        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+                        db1_acc += rs;
+                    }
+                    {   // B (64 rows x 16 samples) = x_k^T : thread (sample s = tid % 16, part p = tid / 16):
+                        // p < 8: feature float4 p (rows 20 + 4p ..), p < 10: sin/cos j = p (rows p, 10 + p), p >= 10: zero rows 52..63
+                        if (p < 8) {
+                            const float fv[4] = {cur.f4.x, cur.f4.y, cur.f4.z, cur.f4.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                float hi, lo;
+                                tc::split_tf32(fv[c], hi, lo);
+                                const uint32_t o = tc::canon_off_floats(20 + 4 * p + c, s, 64);
+                                sB[o] = hi; sB[64 * KC + o] = lo;
+                            }
+                        }
+                        if (p < 10) {
+                            float sn = 0.f, cs = 0.f;
+                            if (cur.id >= 0) {
+                                const float* pp = sPos + (m0c + s) * 4;
+                                const float rx = __fmul_rn(kTwoPi, __fsub_rn(cur.cx, pp[0]));
+                                const float ry = __fmul_rn(kTwoPi, __fsub_rn(cur.cy, pp[1]));
+                                const float rz = __fmul_rn(kTwoPi, __fsub_rn(cur.cz, pp[2]));
+                                sincosf(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
+                            }
+                            float hi, lo;
+                            const uint32_t o1 = tc::canon_off_floats(p, s, 64), o2 = tc::canon_off_floats(10 + p, s, 64);
+                            tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[64 * KC + o1] = lo;
+                            tc::split_tf32(cs, hi, lo); sB[o2] = hi; sB[64 * KC + o2] = lo;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const uint32_t o = tc::canon_off_floats(52 + 2 * (p - 10) + c, s, 64);
+                                sB[o] = 0.f; sB[64 * KC + o] = 0.f;
+                            }
+                        }
+                    }
+                    if (tid < 128) {   // B2 (32 rows x 4 float4) = df_k^T = wn_k * dcc^T
+                        const float4 d = cur.dcc, w = cur.w4;
+                        const float4 v = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
+                        put4(sB2, 32, tid >> 2, 4 * (tid & 3), v);
+                        float sm = sum4(v);
+                        sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                        db2_acc += sm;
+                    }
+                    hand_over();
+                    cur = nxt;
+                }
+            } else if (lane == 0) {
+                for (long long j = 0; j < n_items; ++j) {
+                    const uint32_t sb = mma_wait();
+                    const uint32_t first = (j == 0) ? 0u : 1u;
+                    mma_group(sb + ST_A0, sb + ST_B, 64, 0, 64, 32, first);                // dN1   = dz1^T x
+                    mma_group(sb + ST_A1, sb + ST_B2, 32, 0, 32, 96, first);               // dN2^T = softplus(z1)^T df
+                    mma_done();
                 }
             }
         }
