@@ -318,25 +318,36 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_bwd_tc(Args a, long long n_ti
             // ---- trunk: dh_l -> (store) -> dz_l = dh_l * softplus'(z_l) -> A operand ------------------------------------
 #pragma unroll 1
             for (int l = 4; l >= 0; --l) {
+                // the saved pre-activations of the first 32 columns are requested BEFORE waiting for the layer's MMAs, those of the
+                // second 32 while the first half is being processed: their latency is off the critical path
+                const long long off0 = (((long long)l * n_tiles + tile) * 128 + 64 * h) * 128 + r;
+                float zc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) zc[j] = a.tsave[TL.zT + off0 + j * 128];
                 tc::mbar_wait(d_ready, pd); pd ^= 1; tc::fence_after_sync();
                 const uint32_t reg = (l & 1) ? TP : TQ;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     const int c0 = 64 * h + 32 * c;
-                    float v[32], lo[32];
+                    float v[32], zn[32];
                     tc::tmem_ld32(lb + reg + c0, v);
-                    const long long off = (((long long)l * n_tiles + tile) * 128 + c0) * 128 + r;
+                    const long long off = off0 + (long long)(32 * c) * 128;
+                    if (c == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) zn[j] = a.tsave[TL.zT + off + (32 + j) * 128];
+                    }
                     if (a.want_wgrad) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) a.tbwd[BL.dhT + off + j * 128] = v[j];
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float z = a.tsave[TL.zT + off + j * 128];
-                        tc::split_tf32(v[j] * sp_grad_fast(z), v[j], lo[j]);
-                    }
+                    for (int j = 0; j < 32; ++j) tc::split_tf32(v[j] * sp_grad_fast(zc[j]), v[j], zc[j]);   // zc <- lo
                     tc::tmem_st32(lb + reg + c0, v);
-                    tc::tmem_st32(lb + TR + c0, lo);
+                    tc::tmem_st32(lb + TR + c0, zc);
+                    if (c == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) zc[j] = zn[j];
+                    }
                 }
                 worker_signal(a_ready);
             }
@@ -412,24 +423,37 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_bwd_tc(Args a, long long n_ti
                         }
                     }
                     worker_signal(a_ready);
+                    // z1 of this neighbour: first 32 columns requested before waiting for the MMAs, the rest during the first half
+                    const long long off0 = ((tile * 8 + k) * 128 + 64 * h) * 128 + r;
+                    float zc[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) zc[j] = a.tsave[TL.z1T + off0 + j * 128];
                     // dh1 -> dz1 = dh1 * softplus'(z1) (store for dN1) -> A
                     tc::mbar_wait(d_ready, pd); pd ^= 1; tc::fence_after_sync();
 #pragma unroll 1
                     for (int c = 0; c < 2; ++c) {
                         const int c0 = 64 * h + 32 * c;
-                        float v[32], lo[32];
+                        float v[32], zn[32];
                         tc::tmem_ld32(lb + TQ + c0, v);
-                        const long long off = ((tile * 8 + k) * 128 + c0) * 128 + r;
+                        const long long off = off0 + (long long)(32 * c) * 128;
+                        if (c == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= sp_grad_fast(a.tsave[TL.z1T + off + j * 128]);
+                            for (int j = 0; j < 32; ++j) zn[j] = a.tsave[TL.z1T + off + (32 + j) * 128];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= sp_grad_fast(zc[j]);
                         if (a.want_wgrad) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) a.tbwd[BL.dz1T + off + j * 128] = v[j];
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) tc::split_tf32(v[j], v[j], lo[j]);
+                        for (int j = 0; j < 32; ++j) tc::split_tf32(v[j], v[j], zc[j]);                      // zc <- lo
                         tc::tmem_st32(lb + TQ + c0, v);
-                        tc::tmem_st32(lb + TR + c0, lo);
+                        tc::tmem_st32(lb + TR + c0, zc);
+                        if (c == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) zc[j] = zn[j];
+                        }
                     }
                     worker_signal(a_ready);
                     // dx: columns [0,20) rel-pos embedding, [20,52) feature  (half 0: 0..31, half 1: 32..63)

@@ -350,6 +350,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                     tc::tmem_st32(lb + TR + 32 * h, xv);
                     tc::tmem_st32(lb + TR + 64 + 32 * h, lo);
                     worker_signal(a_ready);
+                    if (k < 7) {                           // next neighbour's feature row / position: into L1 while the MMAs run
+                        const int idn = idx[k + 1];
+                        if (idn >= 0) {
+                            tc::prefetch_l1(a.col_feats + (size_t)idn * 32);
+                            if (h == 0) tc::prefetch_l1(a.cloud_pos + (size_t)idn * 3);
+                        }
+                    }
                     // ---- z1 + b1 -> softplus -> hi (in place, P) / lo (Q)
                     tc::mbar_wait(d_ready, pd); pd ^= 1; tc::fence_after_sync();
 #pragma unroll 1
