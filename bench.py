@@ -252,26 +252,39 @@ def run_ours(args):
     tot_kernel_ms = sum(v[0] for v in prof.values())
     top = max(prof, key=lambda k: prof[k][0])
     top_ms, top_n = prof[top]
-    # samples one launch of the dominant kernel processes (tracker launches see ~TRACK_PIX*S, mapper ~MAP_PIX*S)
-    per_launch_samples = n_prof / max(prof['knn'][1], 1)
-    if top in ('wgrad_tc',):
-        per_launch_samples = MAP_PIX * S                                   # only the mapper's colour-stage iterations launch it
+    # samples one launch of the dominant kernel processes: the tracker launches see TRACK_PIX*S, the mapper's MAP_PIX*S
+    n_track, n_map = TRACK_ITERS * TRACK_PIX * S, MAP_ITERS * MAP_PIX * S
+    launches_of = {'wgrad_tc': MAP_ITERS - GEO_ITERS, 'color_fwd_tc': TRACK_ITERS + MAP_ITERS - GEO_ITERS,
+                   'color_bwd_tc': TRACK_ITERS + MAP_ITERS - GEO_ITERS}
+    samples_of = {'wgrad_tc': (MAP_ITERS - GEO_ITERS) * MAP_PIX * S,
+                  'color_fwd_tc': n_track + (MAP_ITERS - GEO_ITERS) * MAP_PIX * S,
+                  'color_bwd_tc': n_track + (MAP_ITERS - GEO_ITERS) * MAP_PIX * S}
+    per_launch_samples = samples_of.get(top, n_prof) / max(launches_of.get(top, prof['knn'][1]), 1)
+    avg_launch_s = top_ms / max(top_n, 1) * 1e-3
     bytes_per_sample = {'decode_bwd': ALGO_BYTES_BWD, 'color_bwd_tc': ALGO_BYTES_BWD, 'wgrad_tc': ALGO_BYTES_BWD}.get(top, ALGO_BYTES_FWD)
-    achieved = per_launch_samples * bytes_per_sample / (top_ms / max(top_n, 1) * 1e-3) / 1e9
-    # tensor-core view of the same kernel: algorithmic FLOPs of the colour branch (fwd 2 x (96 700 + 86 256) MAC; bwd-data and wgrad the same)
-    tc_flops = {'color_fwd_tc': 2 * 182956, 'color_bwd_tc': 2 * 182956, 'wgrad_tc': 2 * 182956}.get(top)
-    tensor = None
-    if tc_flops:
-        tf = per_launch_samples * tc_flops / (top_ms / max(top_n, 1) * 1e-3) / 1e12
-        tensor = {'achieved_tflops_fp32_equivalent': tf, 'mma_tflops_issued_3xtf32': 3 * tf,
-                  'peak_bf16_tflops': float(peaks.get('bf16_tflops', 1590.0)), 'frac_of_bf16_peak_issued': 3 * tf / float(peaks.get('bf16_tflops', 1590.0)),
-                  'note': 'kind::tf32 runs at half the bf16 rate; 3 MMAs per fp32-accurate product'}
+    hbm_achieved = per_launch_samples * bytes_per_sample / avg_launch_s / 1e9
     traffic = None
     tj = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tj):
         t = json.load(open(tj)).get(top)
         if t:
             traffic = t['bytes_per_sample'] * per_launch_samples          # scaled to this launch size; source in profiles/traffic.json
+    hbm_view = {'achieved': hbm_achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_achieved / hbm_peak,
+                'algorithmic_bytes_per_sample': bytes_per_sample}
+    # colour branch (the tcgen05 kernels): 182 956 MAC per sample and pass, issued three times (3xTF32) on kind::tf32 MMAs
+    tc_flops = {'color_fwd_tc': 2 * 182956, 'color_bwd_tc': 2 * 182956, 'wgrad_tc': 2 * 182956}.get(top)
+    bf16_peak = float(peaks.get('bf16_tflops', 1590.0))
+    if tc_flops:
+        tf = per_launch_samples * tc_flops / avg_launch_s / 1e12
+        roof = {'bound': 'tensor', 'kernel': top, 'achieved': 3 * tf, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': 3 * tf / bf16_peak,
+                'traffic': traffic, 'peak_source': peak_src,
+                'note': 'achieved = tf32 MMA FLOP/s issued (3 MMAs per fp32-accurate product); peak = measured dense bf16 (kind::tf32 runs at half of it)',
+                'fp32_equivalent_tflops': tf, 'hbm': hbm_view}
+    else:
+        roof = {'bound': 'hbm', 'kernel': top, 'traffic': traffic, 'peak_source': peak_src, **hbm_view}
+    roof.update({'samples_per_launch': per_launch_samples, 'avg_launch_ms': avg_launch_s * 1e3,
+                 'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
+                 'fp32_tflops_fwd_bwd_all_kernels': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12})
     out = {
         'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': value, 'unit': 'samples/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -286,12 +299,7 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clk,
-        'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_sample': bytes_per_sample, 'samples_per_launch': per_launch_samples,
-                     'avg_launch_ms': top_ms / max(top_n, 1),
-                     'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
-                     'fp32_tflops_fwd_bwd': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12, 'tensor': tensor},
+        'roofline': roof,
         'step_ms': [round(x, 1) for x in per_step], 'step_ms_e2e': [round(x, 1) for x in per_step_e2e],
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
