@@ -374,9 +374,12 @@ class CpuScene:
         return samples
 
 
+CPU_TRACK_ITERS, CPU_MAP_ITERS = 20, 8            # bounded sample of the frame step for the CPU legs (~10 s on the host cores)
+
+
 def cpu_baseline_sample(n_points):
-    """Bounded sample of the same workload on the host cores: 1 tracking iteration (1500 rays) + 1 mapping iteration
-    (2000 rays, colour stage), after untimed warm-ups that also pick the faster of {all, 32} torch threads."""
+    """Bounded sample of the same workload on the host cores: 20 tracking iterations (1500 rays) + 8 mapping iterations
+    (5000 rays, colour stage), after untimed warm-ups that also pick the faster of {all, 32} torch threads."""
     sc = CpuScene(n_points, 3)
     times = {}
     for k, th in enumerate([os.cpu_count()] + ([32] if os.cpu_count() > 32 else [])):
@@ -387,11 +390,11 @@ def cpu_baseline_sample(n_points):
     threads = min(times, key=times.get)
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
-    n = sc.step(2, 1, 1, 2000)
+    n = sc.step(2, CPU_TRACK_ITERS, CPU_MAP_ITERS, MAP_PIX)
     dt = time.perf_counter() - t0
     return {'value': n / dt, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-            'sample': f'1 tracking iteration x 1500 rays + 1 mapping iteration x 2000 rays (colour stage), fwd+loss+bwd+Adam, '
-                      f'{n_points}-point cloud, S=5, torch {torch.__version__} CPU ({threads} of {os.cpu_count()} threads) + scipy '
+            'sample': f'{CPU_TRACK_ITERS} tracking iterations x {TRACK_PIX} rays + {CPU_MAP_ITERS} mapping iterations x {MAP_PIX} rays (colour stage), '
+                      f'fwd+loss+bwd+Adam, {n_points}-point cloud, S=5, torch {torch.__version__} CPU ({threads} of {os.cpu_count()} threads) + scipy '
                       f'cKDTree exact kNN; {dt:.1f} s', 'seconds': dt}
 
 
@@ -416,18 +419,19 @@ def run_reference(args):
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
     samples = 0
+    r_track, r_map = max(CPU_TRACK_ITERS // 2, 1), max(CPU_MAP_ITERS // 2, 1)
     for k in range(args.steps):
-        samples += sc.step(args.warmup + k, 1, 1, 500)
+        samples += sc.step(args.warmup + k, r_track, r_map, MAP_PIX)
     dt = time.perf_counter() - t0
     v = samples / dt
-    sample = ('per step: 1 tracking iteration x 1500 rays + 1 mapping iteration x 500 rays (colour stage), fwd+loss+bwd+Adam on the '
-              f'host cores ({threads} torch threads of {os.cpu_count()}; oracle port of the reference, exact cKDTree kNN)')
+    sample = (f'per step: {r_track} tracking iterations x {TRACK_PIX} rays + {r_map} mapping iterations x {MAP_PIX} rays (colour stage), '
+              f'fwd+loss+bwd+Adam on the host cores ({threads} torch threads of {os.cpu_count()}; oracle port of the reference, exact cKDTree kNN)')
     out = {'impl': 'reference', 'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': v,
            'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dt * 1e3 / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': 'C2 Replica-office0-like frame (same scene/frames as the CUDA arm); each step is a bounded '
-                                  'sample: 1 tracking iteration x 1500 rays + 1 mapping iteration x 500 rays',
+                                  f'sample: {r_track} tracking iterations x {TRACK_PIX} rays + {r_map} mapping iterations x {MAP_PIX} rays',
                       'points': args.points},
            'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
            'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
