@@ -204,6 +204,10 @@ def timed_steps(scene, steps, first, from_host, dist):
 
 def run_ours(args):
     from point_slam_b200 import _lib
+    # keep stdout clean for the ONE JSON line: libraries that printf to fd 1 (e.g. the NCCL version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -306,7 +310,8 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline_sample(args.points)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + '\n').encode())
     if dist is not None:
         dist.destroy_process_group()
 
