@@ -148,7 +148,7 @@ typedef struct psl_decode_cfg {
     int32_t min_nn;           /* pointcloud.min_nn_num (2)                                           */
     int32_t r2_group;         /* r2[m / r2_group]; ignored when r2 == NULL                            */
     int32_t is_tracker;       /* backward only: propagate to pos through the recomputed D (:143-148) */
-    int32_t reserved;
+    int32_t reserved;         /* bit 0 (psl_decode_fwd, geometry stage): write only raw[:,3] (the colour kernel owns raw[:,0:3]) */
     double r2_scalar;
 } psl_decode_cfg;
 

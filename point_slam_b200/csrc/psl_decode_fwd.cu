@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_fwd(DecodeArgs a, long
                 }
                 if (a.cfg.rgb_mode != PSL_RGB_RAW) { r = sigmoidf_(r); g = sigmoidf_(g); b = sigmoidf_(b); }
             }
-            reinterpret_cast<float4*>(a.raw)[m0 + lane] = make_float4(r, g, b, occ);
+            if (a.cfg.reserved & 1) a.raw[(m0 + lane) * 4 + 3] = occ;        // occupancy only: rgb belongs to a concurrent colour kernel
+            else reinterpret_cast<float4*>(a.raw)[m0 + lane] = make_float4(r, g, b, occ);
         }
         __syncwarp();
     }

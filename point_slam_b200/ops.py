@@ -5,6 +5,7 @@ in libpointslam_b200.so.  There is no CPU / eager fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -177,6 +178,15 @@ class RenderSettings:
 USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
+OVERLAP_BRANCHES = os.environ.get('PSL_OVERLAP', '1') != '0'  # geometry kernel on a forked stream next to the colour kernel
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 class PackedDecoder:
@@ -236,18 +246,27 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         if tc_bwd:
             tsave = torch.empty(lib.psl_tc_save_floats(M, cfg.encode_rel_pos), dtype=torch.float32, device=dev)
     if use_tc:
-        # geometry branch (fp32 FFMA kernel: occupancy, has_nb, geometry activations) then the colour branch on tcgen05
+        # the colour branch on tcgen05 and the geometry branch (fp32 FFMA kernel: occupancy, has_nb, geometry activations) are
+        # independent (they write different words of `raw`): the geometry kernel runs on a forked stream and fills the SMs
+        # the colour kernel's partial last wave leaves idle (25 000 samples = 196 tiles on 148 SMs; tracking: 59 tiles)
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 0, cfg.r2_scalar)
-        L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                                   L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
-                                   L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd[geometry]')
+                           cfg.is_tracker, 1, cfg.r2_scalar)       # reserved bit 0: occupancy only, rgb belongs to the colour kernel
         blob = pk.blob
         if not prepacked:
             L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if OVERLAP_BRANCHES else None
+        if side is not None:
+            side.wait_stream(main)                       # fork: everything issued so far (kNN, packing) is visible to the side stream
         L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                      L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
                                      None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                       L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
+                                       L.ptr(has_nb), L.ptr(save), L.stream()), 'psl_decode_fwd[geometry]')
+        if side is not None:
+            main.wait_stream(side)                       # join
         return raw, has_nb, save, tsave, pstruct
     L.check(lib.psl_decode_fwd(C.byref(cfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(rand_geo), L.ptr(rand_col),
