@@ -328,23 +328,40 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         dpos_col = torch.empty((M, 3), dtype=torch.float32, device=dev) if want_pos else None
         want_cparams = any(w and name.startswith('c_') for w, name in zip(want, L_PARAM_NAMES))
         grid_a = C.c_int32(0)
+        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
+                           cfg.is_tracker, 0, cfg.r2_scalar)
+
+        def geometry_backward(dwn_extra, dpos_extra):
+            L.check(lib.psl_decode_bwd(C.byref(gcfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
+                                       L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), None, None, L.ptr(raw),
+                                       L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), None, None,
+                                       C.byref(gstruct), None, L.ptr(dwn_extra), L.ptr(dpos_extra), L.ptr(ws), ws_bytes, L.stream()),
+                    'psl_decode_bwd[geometry]')
+
+        # Without a position gradient (mapping) the geometry branch needs nothing from the colour branch -- the IDW-weight chain
+        # rule, which consumes the colour branch's d(weights), only feeds d_pos -- so it runs on a forked stream and fills the SMs
+        # that the colour kernel's partial last wave leaves idle.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
+        if side is not None:
+            side.wait_stream(main)
         L.check(lib.psl_color_bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                      L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
                                      L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
                                      int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')
+        if side is not None:
+            with torch.cuda.stream(side):
+                geometry_backward(None, None)
         if want_cparams or want_affine:
             wsf = lib.psl_wgrad_tc_ws_floats(M)
             wws = torch.empty(wsf, dtype=torch.float32, device=dev)
             L.check(lib.psl_wgrad_tc(C.byref(cfg), C.byref(pstruct), L.ptr(pos), M, L.ptr(I), L.ptr(cloud_pos), L.ptr(col),
                                      L.ptr(tsave), L.ptr(tbwd), grid_a.value, C.byref(gstruct), L.ptr(d_aff), L.ptr(wws), wsf,
                                      L.stream()), 'psl_wgrad_tc')
-        gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 0, cfg.r2_scalar)
-        L.check(lib.psl_decode_bwd(C.byref(gcfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
-                                   L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), None, None, L.ptr(raw),
-                                   L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), None, None,
-                                   C.byref(gstruct), None, L.ptr(dwn_col), L.ptr(dpos_col), L.ptr(ws), ws_bytes, L.stream()),
-                'psl_decode_bwd[geometry]')
+        if side is not None:
+            main.wait_stream(side)
+        else:
+            geometry_backward(dwn_col, dpos_col)
     else:
         L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
                                    L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
