@@ -7,8 +7,10 @@
 //   a small finalize kernel combines them into the reference-layout gradients.
 // Operands come from the tile-transposed buffers written by the forward / backward-data kernels (psl_tc_layout.cuh), so
 // staging is a 16-byte load, an elementwise function, the tf32 hi/lo split and two 16-byte shared-memory stores; all
-// operands are K-major (K = sample).  Accumulators stay in TMEM across all tiles of a CTA (persistent), one partial
-// buffer per CTA, fixed-order reduction -> deterministic.
+// operands are K-major (K = sample).  Work unit = one 16-sample chunk of a tile; every CTA owns a contiguous range of units,
+// stages them through a 3-deep ring of operand images (the workers fill stage i+1, i+2 while the MMAs of stage i run; the
+// global operands of the next item are already in registers) and keeps its accumulators in TMEM over the whole range;
+// one partial buffer per CTA, fixed-order reduction -> deterministic.
 #include "psl_decode.cuh"
 #include "psl_tc.cuh"
 #include "psl_tc_layout.cuh"
@@ -89,25 +91,6 @@ __device__ __forceinline__ float rows128(float* dstA, const float* __restrict__ 
     rs += __shfl_xor_sync(0xffffffffu, rs, 1);
     return rs;                                      // row sum over the chunk (both threads of a row hold it)
 }
-// A0 = (dh * softplus'(z))^T, A1 = dh^T from one pass over dh and z; returns the two row sums
-__device__ __forceinline__ void stage_dz_dh(float* dA0, float* dA1, const float* __restrict__ DH, const float* __restrict__ Z, int m0c,
-                                            int tid, float& db, float& dbc) {
-    const int row = tid >> 1, k0 = (tid & 1) * 8;
-    float sdz = 0.f, sdh = 0.f;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const float4 h = *reinterpret_cast<const float4*>(DH + row * 128 + m0c + k0 + 4 * q);
-        const float4 z = *reinterpret_cast<const float4*>(Z + row * 128 + m0c + k0 + 4 * q);
-        const float4 d = make_float4(h.x * spg_fast(z.x), h.y * spg_fast(z.y), h.z * spg_fast(z.z), h.w * spg_fast(z.w));
-        put4(dA0, 128, row, k0 + 4 * q, d);
-        put4(dA1, 128, row, k0 + 4 * q, h);
-        sdz += sum4(d); sdh += sum4(h);
-    }
-    sdz += __shfl_xor_sync(0xffffffffu, sdz, 1);
-    sdh += __shfl_xor_sync(0xffffffffu, sdh, 1);
-    db += sdz; dbc += sdh;
-}
-
 struct TrunkRegs { float4 h[2], z[2], zp[2], c; };
 struct NbrRegs { float4 dz[2], z1[2], f4, dcc, w4; float cx, cy, cz; int id; };
 

@@ -313,3 +313,54 @@ def test_fused_graphs_run_and_optimise():
     fm.begin_frame(idx[: idx.shape[0] // 2], [cur] + scene.keyframes)    # a different frustum re-uses the graphs
     le = float(fm.run('color', 3))
     assert np.isfinite(le) and len(fm.graphs) == n_graphs
+
+
+def test_feat_scatter_mapped_equals_dense_scatter_on_selected_rows():
+    """psl_feat_scatter_mapped writes the compact gradient of a row subset; per row the pairs are summed in the same (pair)
+    order as the dense scatter, so the selected rows are bit-identical and unselected points are dropped."""
+    L, lib = _lib()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    N, M, U = 20000, 6000, 3000
+    I = torch.randint(0, N, (M, 8), device=DEV, generator=g, dtype=torch.int32)
+    I[torch.rand(M, 8, device=DEV, generator=g) < 0.2] = -1
+    wn = torch.rand(M, 8, device=DEV, generator=g)
+    wn[I < 0] = 0.0
+    wn[torch.rand(M, 8, device=DEV, generator=g) < 0.1] = 0.0
+    d_cg = torch.randn(M, 32, device=DEV, generator=g)
+    d_colpair = torch.randn(M, 8, 32, device=DEV, generator=g)
+    ws_bytes = lib.psl_feat_scatter_ws_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    dg = torch.zeros(N, 32, device=DEV); dc = torch.zeros(N, 32, device=DEV)
+    L.check(lib.psl_feat_scatter(L.ptr(I), M, N, L.ptr(wn), L.ptr(d_cg), L.ptr(d_colpair), None, L.ptr(dg), L.ptr(dc), L.ptr(ws),
+                                 ws_bytes, L.stream()), 'psl_feat_scatter')
+    rows = torch.randperm(N, device=DEV, generator=g)[:U]
+    row_map = torch.full((N,), -1, dtype=torch.int32, device=DEV)
+    row_map[rows] = torch.arange(U, dtype=torch.int32, device=DEV)
+    cap = 4096                                               # capacity larger than U: the tail stays zero
+    mg = torch.zeros(cap, 32, device=DEV); mc = torch.zeros(cap, 32, device=DEV)
+    L.check(lib.psl_feat_scatter_mapped(L.ptr(I), M, L.ptr(row_map), cap, L.ptr(wn), L.ptr(d_cg), L.ptr(d_colpair), None, L.ptr(mg),
+                                        L.ptr(mc), L.ptr(ws), ws_bytes, L.stream()), 'psl_feat_scatter_mapped')
+    assert torch.equal(mg[:U], dg[rows]) and torch.equal(mc[:U], dc[rows])
+    assert float(mg[U:].abs().max()) == 0.0 and float(mc[U:].abs().max()) == 0.0
+    assert float(dg.abs().sum()) > 0
+    # reference semantics: index_put_(accumulate) of w * d_cg into feats[I] (decoder.py:164), fp64 for an order-free check
+    ref = torch.zeros(N, 32, device=DEV, dtype=torch.float64)
+    valid = (I >= 0) & (wn != 0)
+    contrib = (wn[..., None].double() * d_cg[:, None, :].double())[valid]
+    ref.index_put_((I[valid].long(),), contrib, accumulate=True)
+    assert float((dg.double() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+
+
+def test_shell_entry_points_reject_bad_arguments():
+    L, lib = _lib()
+    d = torch.zeros(9000, device=DEV); o = torch.zeros(9000, device=DEV); m = torch.zeros(9000, dtype=torch.uint8, device=DEV)
+    assert lib.psl_depth_gate(L.ptr(d), 9000, L.ptr(o), L.ptr(m), L.stream()) != 0
+    assert b'8192' in lib.psl_last_error()
+    assert lib.psl_depth_gate(None, 10, L.ptr(o), L.ptr(m), L.stream()) != 0
+    loss = torch.zeros((), device=DEV)
+    assert lib.psl_shell_loss(0, 10, L.ptr(d), L.ptr(m), None, L.ptr(d), None, None, None, 0.5, L.ptr(loss), L.ptr(o), None, L.stream()) != 0   # tracking needs var
+    assert lib.psl_shell_loss(1, 10, L.ptr(d), L.ptr(m), None, L.ptr(d), None, None, None, 0.1, L.ptr(loss), L.ptr(o), None, L.stream()) != 0   # mapping needs ray_mask
+    pix = torch.zeros(4, dtype=torch.int64, device=DEV)
+    assert lib.psl_sample_rays(L.ptr(pix), 1, 4, 480, 640, 0, 0, 640, None, None, L.ptr(d), L.ptr(d), None, 1., 1., 0., 0., L.ptr(o), L.ptr(o),
+                               L.ptr(o), L.ptr(o), None, L.stream()) != 0                                                     # neither cam nor c2w
+    torch.cuda.synchronize()
