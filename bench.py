@@ -228,11 +228,16 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
     # per-kernel device time of one more step (CUDA events on the launching stream inside the library)
     # (the same static-shape iterations launched eagerly: graph replays bypass the host-side event hooks)
+    # with the geometry kernels launched in-line (no stream fork): a forked kernel's slot would include the time it
+    # waits for free SMs and could be mistaken for the dominant kernel
+    from point_slam_b200 import ops as _ops
     l0 = lib.psl_launch_count()
+    overlap, _ops.OVERLAP_BRANCHES = _ops.OVERLAP_BRANCHES, False
     _lib.timing_enable(True)
     n_prof = scene.step(args.warmup, False, graphs=False)
     prof = _lib.timing_collect()
     _lib.timing_enable(False)
+    _ops.OVERLAP_BRANCHES = overlap
     launches = (lib.psl_launch_count() - l0) * args.steps           # kernels of this library per step x timed steps
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)

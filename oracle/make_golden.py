@@ -233,7 +233,38 @@ def run_aux(scene):
     print('aux: add kept', int(k1), int(k2), 'near_pcl invalid', int(inv.sum()), '/ 96')
 
 
+def run_frustum():
+    """Mapper.get_mask_from_c2w (src/Mapper.py:120-168) of the unmodified reference on a whole-room cloud: two poses of a
+    quarter-size camera, sensor depth with zero-depth holes, the shipped frustum_edge (-4) and a positive one."""
+    import types
+    Mapper = H.load_mapper_class()
+    intr = dict(H=120, W=160, fx=INTR['fx'] / 4, fy=INTR['fy'] / 4, cx=INTR['cx'] / 4, cy=INTR['cy'] / 4)
+    cloud = synth.make_cloud(30000, seed=77)
+    rng = np.random.default_rng(78)
+    extra = rng.uniform([-1, -1, -1], [7, 5, 3.7], (2000, 3)).astype(np.float32)      # outside the walls / behind surfaces
+    cloud = np.concatenate([cloud, extra], 0)
+    out = dict(cloud=cloud, intr=np.array([intr[k] for k in ('H', 'W', 'fx', 'fy', 'cx', 'cy')], np.float64))
+    poses = [synth.look_at([1.6, 2.6, 1.1], [1.5, 0.0, 0.7]), synth.trajectory(7, seed=5)[3]]
+    for k, (c2w, edge) in enumerate(zip(poses, (-4, 10))):
+        depth, _ = synth.make_frame(c2w, intr)
+        depth = depth.astype(np.float32)
+        depth[rng.random(depth.shape) < 0.04] = 0.0
+        depth[:9, :13] = 0.0                                   # a zero-depth corner: border taps mix with it
+        npc = types.SimpleNamespace(cloud_pos=lambda c=cloud: c.tolist())
+        me = types.SimpleNamespace(H=intr['H'], W=intr['W'], fx=intr['fx'], fy=intr['fy'], cx=intr['cx'], cy=intr['cy'],
+                                   npc=npc, frustum_edge=edge)
+        c2w_t = torch.from_numpy(c2w).float()
+        idx = Mapper.get_mask_from_c2w(me, c2w_t, depth)
+        out[f'c2w{k}'], out[f'depth{k}'], out[f'edge{k}'] = c2w_t.numpy(), depth, np.int64(edge)
+        out[f'indices{k}'] = np.asarray(idx, np.int64)
+        print(f'frustum {k}: {len(idx)} of {cloud.shape[0]} points selected (edge {edge})')
+    np.savez_compressed(os.path.join(OUT, 'frustum.npz'), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'frustum':        # only the newest fixture (the others stay byte-identical)
+        run_frustum()
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     scene = make_scene()
@@ -254,6 +285,7 @@ def main():
              use_cam_tensor=True, exposure='feat')
     run_case('exposure_mapper_raw', scene, scn, None, 'color', False, 96, seed=15)
     run_aux(scene)
+    run_frustum()
 
 
 if __name__ == '__main__':

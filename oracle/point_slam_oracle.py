@@ -443,3 +443,61 @@ def add_points(cloud_pos, rays_o, rays_d, gt_depth, radius_add=0.04, dynamic_rad
     z = near_surface * Ds * (1. - t) + far_surface * Ds * t
     pts = (o[..., None, :] + d[..., None, :] * z[..., :, None])[keep].reshape(-1, 3)
     return keep, pts
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frustum feature selection
+# ---------------------------------------------------------------------------------------------------------------------
+def remap_bilinear_f32(img: np.ndarray, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """cv2.remap(img, x, y, INTER_LINEAR) for a float32 image and float32 maps, border constant 0, restated from
+    OpenCV's imgproc/src/imgwarp.cpp (RemapInvoker + remapBilinear<Cast<float,float>, ..., float>): coordinates are
+    rounded to 1/32 pixel (cvRound = round-half-even of x*32, non-finite / overflowing values -> INT_MIN), the integer
+    part saturates to int16, weights are the exact products (1-fy)(1-fx) ... of the 1/32 fractions, the four taps
+    (0 outside the image) are accumulated left to right in float32.  Bit-identical to OpenCV 4.13 on the inputs of
+    `oracle/make_golden.py:run_frustum` and on 200 000 random coordinates incl. NaN/inf (checked when this was written)."""
+    H, W = img.shape
+    f32 = np.float32
+    with np.errstate(all='ignore'):
+        sx, sy = np.rint(x.astype(f32) * f32(32)), np.rint(y.astype(f32) * f32(32))
+
+    def to_int(a):
+        bad = ~np.isfinite(a) | (a >= 2.0 ** 31) | (a < -2.0 ** 31)
+        return np.where(bad, -2.0 ** 31, a).astype(np.int64)
+    sx, sy = to_int(sx), to_int(sy)
+    fx, fy = (sx & 31).astype(f32) / f32(32), (sy & 31).astype(f32) / f32(32)
+    ix, iy = np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)
+
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        return np.where(ok, img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], f32(0))
+    one = f32(1)
+    w0, w1, w2, w3 = (one - fy) * (one - fx), (one - fy) * fx, fy * (one - fx), fy * fx
+    return ((tap(iy, ix) * w0 + tap(iy, ix + 1) * w1) + tap(iy + 1, ix) * w2) + tap(iy + 1, ix + 1) * w3
+
+
+def frustum_project(cloud_pos: np.ndarray, w2c: np.ndarray, fx, fy, cx, cy):
+    """Mapper.get_mask_from_c2w, src/Mapper.py:131-147: float64 projection of the cloud (positions come from a Python
+    list, hence float64) with the float32 inverse pose promoted to float64.  -> (u f32, v f32, z f64)."""
+    p = np.asarray(cloud_pos, np.float64).reshape(-1, 3)
+    w = np.asarray(w2c, np.float64)
+    cam = [((w[r, 0] * p[:, 0] + w[r, 1] * p[:, 1]) + w[r, 2] * p[:, 2]) + w[r, 3] for r in range(3)]
+    xc = -cam[0]                                              # :142 flip of the x axis
+    u = (fx * xc + 0.0 * cam[1]) + cx * cam[2]
+    v = (0.0 * xc + fy * cam[1]) + cy * cam[2]
+    z = cam[2] + 1e-5                                         # :144  (uv[:, -1:] = 1*z_cam)
+    with np.errstate(all='ignore'):
+        return (u / z).astype(np.float32), (v / z).astype(np.float32), z
+
+
+def frustum_indices(cloud_pos, c2w_f32, depth, H, W, fx, fy, cx, cy, edge=-4):
+    """Mapper.get_mask_from_c2w (src/Mapper.py:120-168): indices of the points inside the (edge-enlarged) image whose
+    camera depth is in [0, sampled sensor depth + 0.5]; zero sensor depth counts as the frame's largest sampled depth."""
+    w2c = np.linalg.inv(np.asarray(c2w_f32, np.float32))      # :133, float32 LAPACK inverse like the reference
+    u, v, z = frustum_project(cloud_pos, w2c, fx, fy, cx, cy)
+    d = remap_bilinear_f32(np.asarray(depth, np.float32), u, v)
+    mask = (u < W - edge) & (u > edge) & (v < H - edge) & (v > edge)
+    d = d.copy()
+    if d.size:
+        d[d == 0] = np.max(d)                                 # :158-159
+    mask &= (0 <= -z) & (-z <= d + 0.5)                       # float64 vs float32 -> compared in float64
+    return np.nonzero(mask)[0]

@@ -9,6 +9,9 @@ What is stubbed and why:
     EXACT search of `oracle.point_slam_oracle.knn_exact`.  The reference class
     `src.neural_point.NeuralPointCloud` then runs unmodified on top of it.
   * `skimage` is only needed at import time of `src/common.py` (:6-7).
+  * `load_mapper_class()` additionally stubs the import-time-only dependencies of src/Mapper.py (open3d, colorama,
+    matplotlib, torchmetrics, pytorch_msssim) so that the unmodified `Mapper.get_mask_from_c2w` can be called unbound;
+    cv2, numpy and scipy are the real packages.
   * two CPU-only breakages are patched: `quad2rotation`'s `.to(quad.get_device())`
     (src/common.py:238) and `POINT.forward('geometry')`'s `device='cuda:-1'`
     (src/conv_onet/models/decoder.py:499,505).
@@ -174,3 +177,29 @@ def draw_rand_vecs(seed):
     a = torch.zeros([32]).normal_(mean=0, std=0.01)
     b = torch.zeros([32]).normal_(mean=0, std=0.01)
     return a, b
+
+
+def load_mapper_class():
+    """The reference `Mapper` class (src/Mapper.py), imported for its stateless helpers (get_mask_from_c2w)."""
+    assert os.path.isdir(REF_ROOT), 'reference tree not present (this harness only runs in the build container)'
+    _install_stubs()
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    stub('open3d')
+    stub('colorama', Fore=types.SimpleNamespace(), Style=types.SimpleNamespace())
+    stub('matplotlib')
+    stub('matplotlib.pyplot')
+    stub('torchmetrics')
+    stub('torchmetrics.image')
+    stub('torchmetrics.image.lpip', LearnedPerceptualImagePatchSimilarity=object)
+    stub('pytorch_msssim', ms_ssim=None)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    with _cwd(REF_ROOT):
+        import src.Mapper as ref_mapper
+    return ref_mapper.Mapper

@@ -14,7 +14,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, 'libpointslam_b200.so')
+# PSL_LIB: load another build of the same sources (A/B experiments, e.g. one compiled with -DPSL_PRECISE_TRIG)
+LIB_PATH = os.environ.get('PSL_LIB') or os.path.join(_HERE, 'libpointslam_b200.so')
 SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_bwd_tc.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu']
 HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -110,20 +111,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
     """Compile the CUDA sources for sm_100a into point_slam_b200/libpointslam_b200.so (nvcc cross-compiles
-    without a GPU)."""
-    if not force and not needs_build():
+    without a GPU).  `out` / `defines`: an experiment build next to the product one (see PSL_LIB)."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
+    out = out or LIB_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     srcs = [os.path.join(_HERE, 'csrc', f) for f in SOURCES]
-    cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-o', LIB_PATH] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-shared', '-o', out] + srcs
     if verbose:
         print(' '.join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 def load():

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_bwd_tc(Args a, long long n_ti
 #pragma unroll
                     for (int j = 0; j < 20; ++j) {
                         float sn, cs;
-                        sincosf(fmaf(z, Bc[40 + j], fmaf(y, Bc[20 + j], x * Bc[j])), &sn, &cs);
+                        sincos_embed(fmaf(z, Bc[40 + j], fmaf(y, Bc[20 + j], x * Bc[j])), &sn, &cs);
                         const float dcos = j < 12 ? e0[20 + j] : e1[j - 12];
                         const float da = e0[j] * cs - dcos * sn;
                         gx = fmaf(da, Bc[j], gx); gy = fmaf(da, Bc[20 + j], gy); gz = fmaf(da, Bc[40 + j], gz);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_bwd_tc(Args a, long long n_ti
                             float da = 0.f;
                             if (live) {
                                 float sn, cs;
-                                sincosf(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
+                                sincos_embed(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
                                 da = dx[jj] * cs - dx[10 + jj] * sn;
                             }
                             gx = fmaf(da, Br[jj], gx); gy = fmaf(da, Br[12 + jj], gy); gz = fmaf(da, Br[24 + jj], gz);

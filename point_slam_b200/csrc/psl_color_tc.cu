@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
 #pragma unroll
                         for (int jj = 0; jj < 10; ++jj) {
                             float sn = 0.f, cs = 0.f;
-                            if (id >= 0) sincosf(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
+                            if (id >= 0) sincos_embed(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
                             xv[jj] = sn; xv[10 + jj] = cs;
                         }
 #pragma unroll
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_fwd_tc(Args a, long long n_ti
                 for (int j = 0; j < 20; ++j) {
                     const float arg = fmaf(z, Bc[40 + j], fmaf(y, Bc[20 + j], x * Bc[j]));
                     float ehi, elo;
-                    tc::split_tf32(h == 0 ? sinf(arg) : cosf(arg), ehi, elo);
+                    tc::split_tf32(h == 0 ? sin_embed(arg) : cos_embed(arg), ehi, elo);
                     const uint32_t o = tc::canon_off_floats(r, 20 * h + j, 128);
                     sEhi[o] = ehi; sElo[o] = elo;
                 }

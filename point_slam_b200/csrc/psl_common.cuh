@@ -89,6 +89,26 @@ __device__ __forceinline__ float softplus100_fast(float x) {
     const float y = __logf(1.0f + e) * 0.01f;
     return bx > 20.0f ? x : y;
 }
+// sin / cos of a Fourier-embedding argument (|x| up to a few 1e3 rad) for the tensor-core kernels: three-term Cody-Waite
+// reduction by 2*pi (k*C1 exact for |k| < 2^15) and the SFU sin/cos on [-pi, pi] -- absolute error <~ 7e-7 (MUFU 2^-21.4 +
+// 2.5e-7 from the reduction) where sincosf() is ~1 ulp but costs ~35 instructions and a Payne-Hanek slow path in the
+// instruction stream.  fp32 spacing of the argument itself is 2.4e-4 at 4e3 rad, so this is far below the input noise.
+// -DPSL_PRECISE_TRIG restores sincosf (A/B builds, tests/test_gpu_tc.py checks both against the fp64 oracle).
+__device__ __forceinline__ void sincos_embed(float x, float* s, float* c) {
+#ifdef PSL_PRECISE_TRIG
+    sincosf(x, s, c);
+#else
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.28125f, x);
+    r = fmaf(k, -0.0019353071693331003f, r);
+    r = fmaf(k, -1.0253131677018246e-11f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+#endif
+}
+__device__ __forceinline__ float sin_embed(float x) { float s, c; sincos_embed(x, &s, &c); return s; }
+__device__ __forceinline__ float cos_embed(float x) { float s, c; sincos_embed(x, &s, &c); return c; }
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace psl

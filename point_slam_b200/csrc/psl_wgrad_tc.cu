@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                         const float* p = sPos + (m0c + k) * 4;
                         const float x = __fmul_rn(kTwoPi, p[0]), y = __fmul_rn(kTwoPi, p[1]), z = __fmul_rn(kTwoPi, p[2]);
                         float sn, cs;
-                        sincosf(fmaf(z, sVec[40 + jj], fmaf(y, sVec[20 + jj], x * sVec[jj])), &sn, &cs);
+                        sincos_embed(fmaf(z, sVec[40 + jj], fmaf(y, sVec[20 + jj], x * sVec[jj])), &sn, &cs);
                         float hi, lo;
                         const uint32_t o1 = tc::canon_off_floats(erow + jj, k, R), o2 = tc::canon_off_floats(erow + 20 + jj, k, R);
                         tc::split_tf32(sn, hi, lo); sB[o1] = hi; sB[R * KC + o1] = lo;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                                 const float rx = __fmul_rn(kTwoPi, __fsub_rn(cur.cx, pp[0]));
                                 const float ry = __fmul_rn(kTwoPi, __fsub_rn(cur.cy, pp[1]));
                                 const float rz = __fmul_rn(kTwoPi, __fsub_rn(cur.cz, pp[2]));
-                                sincosf(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
+                                sincos_embed(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
                             }
                             float hi, lo;
                             const uint32_t o1 = tc::canon_off_floats(p, s, 64), o2 = tc::canon_off_floats(10 + p, s, 64);

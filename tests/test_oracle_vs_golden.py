@@ -87,3 +87,13 @@ def test_fp64_noise_floor():
     o64 = C.run_oracle(c, torch.float64)
     assert C.rel_err(o32['depth'], o64['depth']) < 1e-5
     assert C.rel_err(o32['color'], o64['color']) < 1e-4
+
+
+def test_frustum_selection_matches_reference():
+    """oracle.frustum_indices == Mapper.get_mask_from_c2w of the unmodified reference (cv2.remap included), bit for bit."""
+    z = np.load(C.GOLDEN + '/frustum.npz')
+    H, W, fx, fy, cx, cy = z['intr']
+    for k in range(2):
+        idx = O.frustum_indices(z['cloud'], z[f'c2w{k}'], z[f'depth{k}'], int(H), int(W), fx, fy, cx, cy, edge=int(z[f'edge{k}']))
+        assert np.array_equal(idx, z[f'indices{k}']), k
+        assert 500 < idx.size < z['cloud'].shape[0] // 2
