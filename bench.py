@@ -140,8 +140,8 @@ class GpuScene:
         self.resident = [self._to_device(f) for f in self.frames_host[N_KEYFRAMES:]]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
         self.out_host = torch.empty(8, dtype=torch.float32).pin_memory()
-        from point_slam_b200 import graphed as G
-        self.G = G
+        from point_slam_b200 import graphed as G, ops
+        self.G, self.ops = G, ops
         self.tracker = G.FusedTracker(self.renderer, self.npc, self.decoders, INTR, TRACK_PIX, device, edge=(100, 100))
         self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, MAP_PIX, device)
 
@@ -170,7 +170,9 @@ class GpuScene:
             loss = tr.loss
         cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn,
                    c2w=torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True))
-        idx = IT.frustum_indices(npc.cloud_pos_tensor(), cur['c2w'], INTR)
+        # frustum feature selection with the sensor-depth test, Mapper.get_mask_from_c2w (library kernel, one 4-byte D2H)
+        idx = self.ops.frustum_select(npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
+                                      INTR['cx'], INTR['cy'], edge=-4)
         self.mapper.begin_frame(idx, [cur] + self.keyframes)
         if graphs:
             self.mapper.run('geometry', GEO_ITERS)
@@ -183,6 +185,42 @@ class GpuScene:
             self.out_host[:7].copy_(tr.cam.detach(), non_blocking=True)
             self.out_host[7:8].copy_(loss.reshape(1), non_blocking=True)
         return (TRACK_ITERS * TRACK_PIX + MAP_ITERS * (MAP_PIX // (1 + N_KEYFRAMES)) * (1 + N_KEYFRAMES)) * S
+
+
+def _map_maintenance_ms(self, k, reps=5):
+    """Device time of the two per-mapped-frame map updates on frame k: frustum selection over the whole
+    cloud and add_neural_points for `pixels_adding` = 6000 rays (point_slam.yaml:61) incl. the hash rebuild.  Run after the
+    timed region: the add may grow the cloud."""
+    from point_slam_b200.src import common
+    d = self.device
+    fh = self.frames_host[N_KEYFRAMES + k]
+    fr = self.resident[k]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sel = added = 0
+    t_sel = t_add = 0.0
+    g = torch.Generator(device=d).manual_seed(11)
+    for r in range(reps + 1):
+        pix = torch.randint(0, INTR['H'] * INTR['W'], (6000,), device=d, generator=g)
+        j, i = pix // INTR['W'], pix % INTR['W']
+        ro, rd = common.get_rays_from_uv(i.float(), j.float(), fr['c2w'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], d)
+        gd, gc = fr['depth'][j, i], fr['color'][j, i]
+        r_add = fr['dyn_r_query'][j, i] / 2.0
+        ev[0].record()
+        idx = self.ops.frustum_select(self.npc.cloud_pos_tensor(), fh['c2w'], fr['depth'], INTR['H'], INTR['W'], INTR['fx'],
+                                      INTR['fy'], INTR['cx'], INTR['cy'], edge=-4)
+        ev[1].record()
+        ev[2].record()
+        k_add = self.npc.add_neural_points(ro, rd, gd, gc, dynamic_radius=r_add[gd > 0])
+        ev[3].record()
+        torch.cuda.synchronize()
+        if r:                                           # first repetition = warm-up
+            t_sel += ev[0].elapsed_time(ev[1]); t_add += ev[2].elapsed_time(ev[3])
+            sel, added = int(idx.numel()), added + int(k_add)
+    return {'frustum_select_ms': t_sel / reps, 'selected_points': sel, 'add_neural_points_ms': t_add / reps,
+            'rays_per_add': 6000, 'locations_added_total': added, 'points': self.npc.pts_num()}
+
+
+GpuScene.map_maintenance_ms = _map_maintenance_ms
 
 
 def timed_steps(scene, steps, first, from_host, dist):
@@ -239,6 +277,7 @@ def run_ours(args):
     _lib.timing_enable(False)
     _ops.OVERLAP_BRANCHES = overlap
     launches = (lib.psl_launch_count() - l0) * args.steps           # kernels of this library per step x timed steps
+    maint = scene.map_maintenance_ms(args.warmup) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,6 +351,7 @@ def run_ours(args):
         'step_ms': [round(x, 1) for x in per_step], 'step_ms_e2e': [round(x, 1) for x in per_step_e2e],
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
+        'map_maintenance': maint,
     }
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline_sample(args.points)
@@ -375,7 +415,9 @@ class CpuScene:
                                         cur['dyn_r_query'], INTR, TRACK_PIX, 'cpu', self.geo, self.col, self.cloud,
                                         edge=(100, 100))
             samples += n * S
-        idx = IT.frustum_indices(self.cloud, cur['c2w'], INTR)
+        from oracle import point_slam_oracle as O
+        idx = torch.from_numpy(O.frustum_indices(self.cloud.numpy(), cur['c2w64'].astype(np.float32), cur['depth'].numpy(), INTR['H'],
+                                                 INTR['W'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], edge=-4))
         state = IT.MapperState(self, self.decoders, idx)
         for it in range(map_iters):
             _, n = IT.mapper_iteration(self.render, self, self.decoders, state, [cur, self.frames[0]], INTR, map_pix, 'cpu',

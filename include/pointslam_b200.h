@@ -283,6 +283,33 @@ int psl_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   int32_t width, int32_t* step, float lr, float beta1, float beta2, float eps, int32_t zero_grad,
                   psl_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * map maintenance between renders
+ * ------------------------------------------------------------------------- */
+/* NeuralPointCloud.add_neural_points (src/neural_point.py:91-167) without host round trips.  For ray i with
+ * gt_depth[i] > 0 the surface point p = o + d*depth is tested against the indexed cloud: kept iff NO point has
+ * D < r^2 (canonical fp32 D, float64 compare; r^2 = r2_valid[rank of i among the depth > 0 rays] or r2_scalar;
+ * an empty grid keeps every valid ray, :116).  Kept rays are compacted IN ORDER: ray with keep-rank j writes
+ * input_pos[j] = p, input_rgb[j] = 255*gt_color[i] (both optional) and its n_add points o + d*z_s to
+ * new_pos[j*n_add + s], z_s = near*depth*(1-steps[s]) + far*depth*steps[s]  (:135-137, steps = linspace(0,1,n_add)) or
+ * depth + steps[s] when fixed_interval (:131-133, steps = linspace(-0.04,0.04,n_add)).  counts (device, 2 x int32) =
+ * {number of depth > 0 rays, number of kept rays}.  new_pos needs room for n*n_add points.  ws: psl_add_points_ws_bytes(n). */
+size_t psl_add_points_ws_bytes(int64_t n);
+int psl_add_points(const psl_grid* grid_host, const float* rays_o, const float* rays_d, const float* gt_depth,
+                   const float* gt_color /* (n,3) or NULL */, int64_t n, const double* r2_valid, double r2_scalar,
+                   int32_t n_add, int32_t fixed_interval, float near_surface, float far_surface, const float* steps,
+                   float* new_pos, float* input_pos, float* input_rgb, int32_t* counts, void* ws, size_t ws_bytes,
+                   psl_stream_t stream);
+/* Mapper.get_mask_from_c2w (src/Mapper.py:120-168): frustum feature selection.  w2c_host: 12 doubles on the HOST = rows
+ * 0..2 of numpy.linalg.inv(c2w float32) promoted to float64 (the reference inverts in float32 and projects a float64
+ * copy of the cloud).  depth (H,W) float32 sensor depth; the bilinear lookup reproduces cv2.remap(INTER_LINEAR, border 0)
+ * bit for bit; depth must be NaN-free.  mask (n) uint8; indices (optional, room for n) receives np.where(mask)[0] in
+ * ascending order and *count (device int32) its length.  ws: psl_frustum_select_ws_bytes(n). */
+size_t psl_frustum_select_ws_bytes(int64_t n);
+int psl_frustum_select(const float* cloud_pos, int64_t n, const double* w2c_host, double fx, double fy, double cx, double cy,
+                       const float* depth, int32_t H, int32_t W, int32_t edge, uint8_t* mask, int64_t* indices,
+                       int32_t* count, void* ws, size_t ws_bytes, psl_stream_t stream);
+
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
 

@@ -35,7 +35,7 @@ int sm_count();
 
 // optional per-kernel device timing (psl_timing_enable): CUDA events recorded on the launching stream
 enum { T_KNN = 0, T_DECODE_FWD = 1, T_DECODE_BWD = 2, T_COMPOSITE = 3, T_SCATTER = 4, T_PACK = 5, T_REDUCE = 6, T_COLOR_FWD_TC = 7,
-       T_COLOR_BWD_TC = 8, T_WGRAD_TC = 9, T_SHELL = 10, T_COUNT = 11 };
+       T_COLOR_BWD_TC = 8, T_WGRAD_TC = 9, T_SHELL = 10, T_MAP = 11, T_COUNT = 12 };
 struct TimingScope {
     int slot;
     cudaStream_t st;

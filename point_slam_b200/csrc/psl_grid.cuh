@@ -1,0 +1,42 @@
+// Device-side view of the spatial hash (K0) and its cell lookup, shared by the kNN kernels (psl_grid.cu) and the map
+// maintenance kernels (psl_map.cu).
+#pragma once
+#include "psl_common.cuh"
+
+namespace psl {
+
+struct GridDev {
+    const float4* pts;
+    const uint64_t* tkeys;
+    const uint2* tvals;
+    uint32_t mask;
+    int n;
+    float inv_cell;
+    float r_small;      // radius of the first search pass (0 = single pass with the full query radius)
+};
+
+__device__ __forceinline__ uint2 grid_lookup(const GridDev& g, uint64_t key) {
+    uint32_t slot = (uint32_t)mix64(key) & g.mask;
+    for (;;) {
+        const uint64_t k = __ldg(g.tkeys + slot);
+        if (k == key) return __ldg(g.tvals + slot);
+        if (k == kEmptyKey) return make_uint2(0u, 0u);
+        slot = (slot + 1) & g.mask;
+    }
+}
+
+static inline int make_grid_dev(const psl_grid* gh, GridDev* g) {
+    PSL_REQUIRE(gh != nullptr, "grid is NULL");
+    PSL_REQUIRE(gh->n >= 0 && gh->cell > 0.f, "grid not built");
+    PSL_REQUIRE(gh->n == 0 || (gh->capacity && (gh->capacity & (gh->capacity - 1)) == 0), "capacity must be 2^k");
+    g->pts = reinterpret_cast<const float4*>(gh->sorted_pts);
+    g->tkeys = gh->table_keys;
+    g->tvals = reinterpret_cast<const uint2*>(gh->table_vals);
+    g->mask = gh->capacity ? gh->capacity - 1 : 0;
+    g->n = gh->n;
+    g->inv_cell = 1.0f / gh->cell;
+    g->r_small = gh->r_small;
+    return 0;
+}
+
+}  // namespace psl

@@ -123,7 +123,8 @@ class SpatialHash:
 def _r2_args(radius, dynamic_radius, M_groups, device):
     """(r2 tensor or None, r2_scalar) with the comparison semantics of neural_point.py:208-213."""
     if dynamic_radius is not None:
-        r2 = (dynamic_radius.detach().reshape(-1).to(device=device, dtype=torch.float64) ** 2).contiguous()
+        # squared in the tensor's own dtype (the reference squares before the promoting comparison), then float64
+        r2 = (dynamic_radius.detach().reshape(-1).to(device=device) ** 2).to(torch.float64).contiguous()
         assert r2.shape[0] == M_groups, 'shape mis-match for input points and dynamic radius'
         return r2, 0.0
     return None, float(np.float32(radius ** 2))
@@ -608,3 +609,85 @@ def decode(st: RenderSettings, grid: SpatialHash, params, p, cloud_pos, geo_feat
 
 def composite(raw, z_vals, has_nb=None, coef=0.1):
     return _CompositeFn.apply(raw, z_vals, has_nb, coef)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# map maintenance between renders
+# ------------------------------------------------------------------------------------------------------------------
+_STEPS = {}
+
+
+def _add_steps(n_add: int, fixed_interval: bool, device) -> torch.Tensor:
+    """linspace(0,1,N_add) / linspace(-0.04,0.04,N_add) of neural_point.py:126-131, evaluated by torch on the CPU."""
+    key = (int(n_add), bool(fixed_interval), str(device))
+    if key not in _STEPS:
+        lo, hi = (-0.04, 0.04) if fixed_interval else (0.0, 1.0)
+        _STEPS[key] = torch.linspace(lo, hi, steps=int(n_add), dtype=torch.float32).to(device)
+    return _STEPS[key]
+
+
+def add_points(grid: SpatialHash, rays_o, rays_d, gt_depth, gt_color, new_pos: torch.Tensor, radius: float,
+               dynamic_radius=None, n_add: int = 3, fixed_interval: bool = False, near_surface: float = 0.98,
+               far_surface: float = 1.02):
+    """add_neural_points geometry (neural_point.py:107-145) in one library call, no host synchronisation:
+    writes the kept rays' N_add points, compacted in ray order, into `new_pos` (room for n*n_add points) and returns
+    (counts (2,) int32 device = [#depth>0 rays, #kept rays], input_pos (n,3), input_rgb (n,3)) -- the first counts[1] rows
+    of the two (n,3) tensors are valid.  `dynamic_radius` has one entry per depth > 0 ray, like the reference's call."""
+    lib = L.load()
+    ro, rd, dep = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
+    n = dep.shape[0]
+    dev = ro.device
+    col = _f32c(gt_color).reshape(-1, 3) if gt_color is not None else None
+    assert new_pos.is_contiguous() and new_pos.dtype == torch.float32 and new_pos.numel() >= n * n_add * 3
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    in_pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    in_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if n == 0:
+        return counts, in_pos, in_rgb
+    r2 = None
+    r2s = float(np.float32(radius ** 2))
+    if dynamic_radius is not None:
+        assert dynamic_radius.numel() <= n, 'shape mis-match for input points and dynamic radius'
+        r2 = (dynamic_radius.detach().reshape(-1).to(device=dev) ** 2).to(torch.float64)
+        if r2.shape[0] < n:                # length is checked against #(depth > 0) by the caller once the counts are known
+            r2 = torch.cat([r2, torch.zeros(n - r2.shape[0], dtype=torch.float64, device=dev)])
+        r2 = r2.contiguous()
+    ws_bytes = lib.psl_add_points_ws_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    steps = _add_steps(n_add, fixed_interval, dev)
+    L.check(lib.psl_add_points(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(dep), L.ptr(col), n, L.ptr(r2), r2s,
+                               int(n_add), int(bool(fixed_interval)), float(near_surface), float(far_surface), L.ptr(steps),
+                               L.ptr(new_pos), L.ptr(in_pos), L.ptr(in_rgb), L.ptr(counts), L.ptr(ws), ws_bytes, L.stream()),
+            'psl_add_points')
+    return counts, in_pos, in_rgb
+
+
+def frustum_select(cloud_pos: torch.Tensor, c2w, depth: torch.Tensor, H, W, fx, fy, cx, cy, edge: int = -4,
+                   return_mask: bool = False):
+    """Mapper.get_mask_from_c2w (Mapper.py:120-168) on the device: -> ascending int64 indices of the selected points
+    (a device tensor where the reference returns a Python list; both index the feature tensors the same way).
+    `c2w`: (4,4) or (3,4) pose (tensor / array); it is inverted on the host in float32 like the reference does."""
+    lib = L.load()
+    pos = _f32c(cloud_pos).reshape(-1, 3)
+    n = pos.shape[0]
+    dev = pos.device
+    c = c2w.detach().cpu().numpy() if torch.is_tensor(c2w) else np.asarray(c2w)
+    c = c.astype(np.float32)
+    if c.shape[0] == 3:
+        c = np.concatenate([c, np.array([[0, 0, 0, 1]], np.float32)], 0)
+    w2c = np.linalg.inv(c).astype(np.float64)
+    w = (C.c_double * 12)(*w2c[:3].reshape(-1).tolist())
+    depth = depth if torch.is_tensor(depth) else torch.from_numpy(np.ascontiguousarray(depth))
+    depth = depth.to(device=dev, dtype=torch.float32).contiguous()
+    assert depth.shape == (H, W)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    if n:
+        ws_bytes = lib.psl_frustum_select_ws_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        L.check(lib.psl_frustum_select(L.ptr(pos), n, w, float(fx), float(fy), float(cx), float(cy), L.ptr(depth), int(H), int(W),
+                                       int(edge), L.ptr(mask), L.ptr(idx), L.ptr(count), L.ptr(ws), ws_bytes, L.stream()),
+                'psl_frustum_select')
+    k = int(count.item())                  # the one synchronisation: the caller sizes its optimisable slices with it
+    return (idx[:k], mask.bool()) if return_mask else idx[:k]

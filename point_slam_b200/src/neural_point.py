@@ -1,7 +1,10 @@
 """Drop-in for the reference `src/neural_point.py`: same class name, constructor and the 14 public methods
 (neural_point.py:44-277), backed by a GPU-resident spatial hash and the exact radius-kNN kernel instead of a
-faiss GpuIndexIVFFlat.  Positions live in a device tensor (capacity-doubling) instead of a Python list; the list
-view the reference API promises (`cloud_pos()`, `_cloud_pos`) is materialised lazily.
+faiss GpuIndexIVFFlat.  Positions and the two feature tensors live in capacity-doubling device buffers (the reference
+re-allocates all of them with list `+=` / `torch.cat` on every add, neural_point.py:147-159); the list views the reference
+API promises (`cloud_pos()`, `_cloud_pos`, `input_pos()`, `input_rgb()`) are materialised lazily.  `add_neural_points` is
+one library call (`ops.add_points`: depth mask, add-radius test, ordered compaction, point emission) plus one 8-byte
+device->host read of the counts.
 """
 import numpy as np
 import torch
@@ -51,10 +54,12 @@ class NeuralPointCloud(object):
         self.N_add = pc['N_add']
         self.near_end_surface, self.far_end_surface = pc['near_end_surface'], pc['far_end_surface']
 
-        self._pos = torch.zeros((0, 3), dtype=torch.float32, device=self.device)   # all positions ever appended
+        self._pos_buf = torch.zeros((0, 3), dtype=torch.float32, device=self.device)   # capacity-doubling storage
+        self._pos = self._pos_buf[:0]                                                  # all positions ever appended (view)
         self._pos_list_cache = None
-        self._input_pos = []
-        self._input_rgb = []
+        self._geo_buf = self._col_buf = None
+        self._input_pos_list, self._input_rgb_list = [], []
+        self._input_pending = []           # device chunks (pos, rgb) not yet converted to the host lists
         self._pts_num = 0
         self._indexed = 0                  # number of positions the hash currently covers
         self.geo_feats = None
@@ -73,7 +78,7 @@ class NeuralPointCloud(object):
 
     @_cloud_pos.setter
     def _cloud_pos(self, value):          # offline tools assign a list (get_mesh_tsdf_fusion.py:66)
-        self._pos = torch.as_tensor(value, dtype=torch.float32, device=self.device).reshape(-1, 3)
+        self._pos = torch.as_tensor(value, dtype=torch.float32, device=self.device).reshape(-1, 3)   # adopted by _reserve
         self._pos_list_cache = None
 
     def cloud_pos(self, index=None):
@@ -85,6 +90,32 @@ class NeuralPointCloud(object):
 
     def spatial_hash(self):
         return self._grid
+
+    def _flush_input(self):
+        for p, c in self._input_pending:
+            self._input_pos_list.extend(p.tolist())
+            self._input_rgb_list.extend(c.tolist())
+        self._input_pending = []
+
+    @property
+    def _input_pos(self):
+        self._flush_input()
+        return self._input_pos_list
+
+    @_input_pos.setter
+    def _input_pos(self, value):           # offline tools assign a list (get_mesh_tsdf_fusion.py:67)
+        self._flush_input()
+        self._input_pos_list = value
+
+    @property
+    def _input_rgb(self):
+        self._flush_input()
+        return self._input_rgb_list
+
+    @_input_rgb.setter
+    def _input_rgb(self, value):
+        self._flush_input()
+        self._input_rgb_list = value
 
     def input_pos(self):
         return self._input_pos
@@ -148,54 +179,79 @@ class NeuralPointCloud(object):
         return D, I.long()
 
     # ---- point insertion (neural_point.py:91-167) --------------------------------------------------------------------
+    def _reserve(self, extra):
+        """Room for `extra` more points behind the indexed ones in the position / feature buffers (amortised doubling).
+        Tensors a caller assigned directly (`npc.geo_feats = ...`, `npc._cloud_pos = ...`) are adopted first."""
+        n = self._indexed
+        need = n + int(extra)
+        if self._pos.data_ptr() != self._pos_buf.data_ptr() or self._pos_buf.shape[0] < need:
+            cap = max(need, 2 * self._pos_buf.shape[0], 1024)
+            buf = torch.empty((cap, 3), dtype=torch.float32, device=self.device)
+            buf[:n] = self._pos[:n]
+            self._pos_buf, self._pos = buf, buf[:n]
+        for name, bufname in (('geo_feats', '_geo_buf'), ('col_feats', '_col_buf')):
+            cur, buf = getattr(self, name), getattr(self, bufname)
+            rows = 0 if cur is None else cur.shape[0]
+            foreign = cur is not None and (buf is None or cur.data_ptr() != buf.data_ptr())
+            if buf is None or foreign or buf.shape[0] < rows + int(extra):
+                cap = max(rows + int(extra), 2 * (0 if buf is None else buf.shape[0]), 1024)
+                nbuf = torch.empty((cap, self.c_dim), dtype=torch.float32, device=self.device)
+                if rows:
+                    nbuf[:rows] = cur.detach()
+                setattr(self, bufname, nbuf)
+                if cur is not None:
+                    setattr(self, name, nbuf[:rows])
+
     def add_neural_points(self, batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color, train=False,
                           is_pts_grad=False, dynamic_radius=None):
-        if not batch_rays_o.shape[0]:
+        n_rays = batch_rays_o.shape[0]
+        if not n_rays:
             return 0
-        mask = batch_gt_depth > 0
-        batch_gt_color = batch_gt_color * 255
-        o, d, depth, color = batch_rays_o[mask], batch_rays_d[mask], batch_gt_depth[mask], batch_gt_color[mask]
-        pts_gt = (o[..., None, :] + d[..., None, :] * depth[..., None, None]).reshape(-1, 3)
-        keep = torch.ones(pts_gt.shape[0], device=self.device).bool()
-        if self.index.is_trained:
-            _, _, n_gt = self.find_neighbors_faiss(pts_gt, step='add', is_pts_grad=is_pts_grad,
-                                                   dynamic_radius=dynamic_radius)
-            keep = (n_gt == 0)                                               # no indexed point inside the add radius
-        self._input_pos.extend(pts_gt[keep].tolist())
-        self._input_rgb.extend(color[keep].tolist())
-        depth_rep = depth.unsqueeze(-1).repeat(1, self.N_add)
-        if self.fix_interval_when_add_along_ray:
-            z_vals = depth_rep + torch.linspace(-0.04, 0.04, steps=self.N_add, device=self.device).unsqueeze(0)
-        else:
-            t = torch.linspace(0.0, 1.0, steps=self.N_add, device=self.device)
-            z_vals = self.near_end_surface * depth_rep * (1. - t) + self.far_end_surface * depth_rep * t
-        pts = (o[..., None, :] + d[..., None, :] * z_vals[..., :, None])[keep].reshape(-1, 3)
-        self._pos = torch.cat([self._pos[:self._indexed], pts.float()], 0)
+        self._reserve(n_rays * self.N_add)
+        n0 = self._indexed
+        radius = self.radius_min if is_pts_grad else self.radius_add
+        counts, in_pos, in_rgb = ops.add_points(
+            self._grid if self.index.is_trained else ops.SpatialHash(cell=self._grid.cell), batch_rays_o, batch_rays_d,
+            batch_gt_depth, batch_gt_color, self._pos_buf[n0:], radius, dynamic_radius=dynamic_radius, n_add=self.N_add,
+            fixed_interval=self.fix_interval_when_add_along_ray, near_surface=self.near_end_surface,
+            far_surface=self.far_end_surface)
+        n_valid, n_keep = (int(v) for v in counts.tolist())          # the one host read of this call (8 bytes)
+        if dynamic_radius is not None and self.index.is_trained:
+            assert n_valid == dynamic_radius.shape[0], 'shape mis-match for input points and dynamic radius'
+        n_new = n_keep * self.N_add
+        self._input_pending.append((in_pos[:n_keep], in_rgb[:n_keep]))
+        self._pos = self._pos_buf[:n0 + n_new]
         self._pos_list_cache = None
-        self._pts_num += pts.shape[0]
-        fresh = lambda n: torch.zeros([n, self.c_dim], device=self.device).normal_(mean=0, std=0.1)
-        if self.geo_feats is None:
-            self.geo_feats = fresh(self._pts_num)
-            self.col_feats = fresh(self._pts_num)
-        else:
-            self.geo_feats = torch.cat([self.geo_feats, fresh(pts.shape[0])], 0)
-            self.col_feats = torch.cat([self.col_feats, fresh(pts.shape[0])], 0)
+        self._pts_num += n_new
+        # fresh N(0, 0.1^2) rows drawn in the reference's order: geometry rows first, then colour rows (:150-159)
+        rows = 0 if self.geo_feats is None else self.geo_feats.shape[0]
+        self._geo_buf[rows:rows + n_new].normal_(mean=0, std=0.1)
+        self._col_buf[rows:rows + n_new].normal_(mean=0, std=0.1)
+        self.geo_feats = self._geo_buf[:rows + n_new]
+        self.col_feats = self._col_buf[:rows + n_new]
+        pts = self._pos[n0:]
         self.index.train(pts)
         self.index.add(pts)
-        return torch.sum(keep)
+        return torch.tensor(n_keep, device=self.device)
 
     def append_points(self, pts, geo_rows, col_rows):
         """Replica-side append: positions + their feature rows as produced by the mapping rank's add_neural_points
         (used by point_slam_b200.parallel.apply_delta; no RNG is consumed here)."""
         pts = pts.to(self.device).float().reshape(-1, 3)
-        self._pos = torch.cat([self._pos[:self._indexed], pts], 0)
+        k = pts.shape[0]
+        self._reserve(k)
+        n0 = self._indexed
+        self._pos_buf[n0:n0 + k] = pts
+        self._pos = self._pos_buf[:n0 + k]
         self._pos_list_cache = None
-        self._pts_num += pts.shape[0]
-        g, c = geo_rows.to(self.device), col_rows.to(self.device)
-        self.geo_feats = g.clone() if self.geo_feats is None else torch.cat([self.geo_feats, g], 0)
-        self.col_feats = c.clone() if self.col_feats is None else torch.cat([self.col_feats, c], 0)
-        self.index.train(pts)
-        self.index.add(pts)
+        self._pts_num += k
+        rows = 0 if self.geo_feats is None else self.geo_feats.shape[0]
+        self._geo_buf[rows:rows + k] = geo_rows.to(self.device)
+        self._col_buf[rows:rows + k] = col_rows.to(self.device)
+        self.geo_feats, self.col_feats = self._geo_buf[:rows + k], self._col_buf[:rows + k]
+        new = self._pos[n0:]
+        self.index.train(new)
+        self.index.add(new)
 
     # ---- kNN (neural_point.py:169-215) --------------------------------------------------------------------------------
     def find_neighbors_faiss(self, pos, step='add', retrain=False, is_pts_grad=False, dynamic_radius=None):

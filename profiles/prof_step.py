@@ -22,7 +22,15 @@ src = scene.resident[0]
 tr, mp = scene.tracker, scene.mapper
 tr.load_frame(src['color'], src['depth'], src['dyn_r_query'], bench.cam_tensor_from_c2w(fh['c2w'], 0.01, scene.rng).to(dev))
 cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=src['c2w'])
-idx = IT.frustum_indices(scene.npc.cloud_pos_tensor(), cur['c2w'], bench.INTR)
+INTR = bench.INTR
+
+
+def select():
+    return scene.ops.frustum_select(scene.npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
+                                    INTR['cx'], INTR['cy'], edge=-4)
+
+
+idx = select()
 mp.begin_frame(idx, [cur] + scene.keyframes)
 
 
@@ -42,6 +50,9 @@ run(2, 2)                      # warm-up (lazy init, allocator)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 run(n_track, n_map)
+if os.environ.get('PSL_PROF_MAP', '1') != '0':      # the per-mapped-frame map updates: frustum selection + add_neural_points
+    select()
+    scene.map_maintenance_ms(0, reps=1)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print('done')

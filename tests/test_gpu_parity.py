@@ -188,3 +188,4 @@ def test_add_neural_points_and_sample_near_pcl():
     cp = np.asarray(npc.cloud_pos(), dtype=np.float32)
     assert np.array_equal(cp[n0:n1], z['add_new1']) and np.array_equal(cp[n1:], z['add_new2'])
     assert npc.get_geo_feats().shape[0] == npc.pts_num() == npc.index_ntotal()
+    assert np.array_equal(np.asarray(npc.input_pos(), np.float32), z['add_input_pos'])

@@ -74,3 +74,67 @@ def test_no_cpu_fallback():
     g = ops.SpatialHash(0.08)
     with pytest.raises((AssertionError, RuntimeError)):
         g.build(torch.zeros(10, 3))
+
+
+def test_add_neural_points_bookkeeping_with_stubbed_kernels(monkeypatch):
+    """Host logic of NeuralPointCloud.add_neural_points (capacity-doubling buffers, adoption of caller-assigned tensors,
+    lazy input lists, counts) with the two library calls replaced by the CPU oracle: the final state must equal what the
+    unmodified reference produced (tests/golden/aux.npz).  The CUDA kernels themselves are checked on the GPU by
+    tests/test_gpu_parity.py::test_add_neural_points_and_sample_near_pcl against the same vectors."""
+    from oracle import point_slam_oracle as O
+    from point_slam_b200 import ops
+    from point_slam_b200.src.neural_point import NeuralPointCloud
+
+    def fake_build(self, cloud_pos):
+        self._cloud = cloud_pos.detach().clone().float().reshape(-1, 3)
+        self.n = self._cloud.shape[0]
+        return self
+
+    def fake_add_points(grid, ro, rd, dep, col, new_pos, radius, dynamic_radius=None, n_add=3, fixed_interval=False,
+                        near_surface=0.98, far_surface=1.02):
+        assert not fixed_interval
+        m = dep > 0
+        dyn = None
+        if dynamic_radius is not None:
+            dyn = torch.zeros(dep.shape[0], dtype=dynamic_radius.dtype)
+            dyn[m] = dynamic_radius[:int(m.sum())]             # the kernel reads r2[rank among the depth > 0 rays]
+        cloud = getattr(grid, '_cloud', None)
+        keep, pts = O.add_points(cloud, ro, rd, dep, radius_add=radius, dynamic_radius=dyn, N_add=n_add,
+                                 near_surface=near_surface, far_surface=far_surface)
+        new_pos[:pts.shape[0]] = pts
+        n = dep.shape[0]
+        in_pos, in_rgb = torch.zeros(n, 3), torch.zeros(n, 3)
+        k = int(keep.sum())
+        in_pos[:k] = (ro[m] + rd[m] * dep[m][:, None])[keep]
+        in_rgb[:k] = (col[m] * 255)[keep]
+        return torch.tensor([int(m.sum()), k], dtype=torch.int32), in_pos, in_rgb
+
+    monkeypatch.setattr(ops.SpatialHash, 'build', fake_build)
+    monkeypatch.setattr(ops, 'add_points', fake_add_points)
+    z = np.load(C.GOLDEN + '/aux.npz')
+    scene = C.load_scene()
+    npc = NeuralPointCloud(make_cfg('replica', 'cpu'))
+    npc._cloud_pos = scene['cloud']                         # caller-assigned storage, like the offline tools do
+    npc._pts_num = scene['cloud'].shape[0]
+    npc.geo_feats, npc.col_feats = scene['geo_feats'].clone(), scene['col_feats'].clone()
+    npc.index.add(npc._pos)
+    ro, rd, gd = (torch.from_numpy(z[k]) for k in ('add_rays_o', 'add_rays_d', 'add_depth'))
+    r_add = torch.from_numpy(z['add_r_add'])
+    col = torch.rand(ro.shape[0], 3)
+    n0 = npc.pts_num()
+    k1 = npc.add_neural_points(ro, rd, gd, col, dynamic_radius=r_add[gd > 0])
+    n1 = npc.pts_num()
+    assert torch.equal(npc.get_geo_feats()[:n0], scene['geo_feats'])          # adopted, not lost
+    k2 = npc.add_neural_points(ro, rd, gd, col, is_pts_grad=True)
+    assert int(k1) == int(z['add_kept1']) and int(k2) == int(z['add_kept2'])
+    cp = np.asarray(npc.cloud_pos(), dtype=np.float32)
+    assert np.array_equal(cp[n0:n1], z['add_new1']) and np.array_equal(cp[n1:], z['add_new2'])
+    assert npc.pts_num() == cp.shape[0] == npc.index_ntotal() == npc.get_geo_feats().shape[0] == npc.get_col_feats().shape[0]
+    assert np.array_equal(np.asarray(npc.input_pos(), np.float32), z['add_input_pos'])
+    assert len(npc.input_rgb()) == int(k1) + int(k2)
+    assert npc._geo_buf.shape[0] >= npc.pts_num() and npc.get_geo_feats().data_ptr() == npc._geo_buf.data_ptr()
+    new_rows = npc.get_geo_feats()[n0:]
+    assert 0.05 < float(new_rows.std()) < 0.2                                  # fresh N(0, 0.1^2) rows
+    import pytest
+    with pytest.raises(AssertionError):                                        # the reference's shape assertion (:209)
+        npc.add_neural_points(ro, rd, gd, col, dynamic_radius=r_add)
