@@ -128,3 +128,32 @@ def test_add_points_many_appends_keep_features_and_capacity():
     grown = [b / a for a, b in zip(caps, caps[1:]) if b != a]
     assert grown and min(grown) >= 2.0 and len(grown) < 5
     assert npc.pts_num() == npc.index_ntotal() == npc.get_geo_feats().shape[0]
+
+
+def test_checkpoint_round_trip_restores_the_cloud(tmp_path):
+    """Logger.log -> torch.load -> load_neural_point_cloud into a fresh NeuralPointCloud (the restore sequence of
+    get_mesh_tsdf_fusion.py:64-82): same positions, features, lists and bit-identical kNN answers."""
+    import types
+    from tests.gpu_harness import build_objects
+    from point_slam_b200.src.neural_point import NeuralPointCloud
+    from point_slam_b200.src.utils.Logger import Logger, load_neural_point_cloud
+    z = np.load(C.GOLDEN + '/aux.npz')
+    c = C.load_case('mapper_color')
+    cfg, decoders, npc, renderer = build_objects(c)
+    ro, rd, gd = (torch.from_numpy(z[k]).to(DEV) for k in ('add_rays_o', 'add_rays_d', 'add_depth'))
+    npc.add_neural_points(ro, rd, gd, torch.rand(ro.shape[0], 3, device=DEV), is_pts_grad=True)     # grown cloud: views of buffers
+    m = types.SimpleNamespace(verbose=False, ckptsdir=str(tmp_path), gt_c2w_list=torch.zeros(2, 4, 4),
+                              estimate_c2w_list=torch.zeros(2, 4, 4), decoders=decoders)
+    path = Logger(cfg, None, m).log(3, [], [0], None, npc)
+    ck = torch.load(path, weights_only=False, map_location='cpu')
+    assert ck['geo_feats'].shape[0] == ck['pts_num'] == len(ck['cloud_pos']) == npc.pts_num()
+    assert ck['geo_feats'].untyped_storage().nbytes() == npc.pts_num() * 32 * 4
+    npc2 = NeuralPointCloud(cfg)
+    assert load_neural_point_cloud(npc2, ck, DEV) == npc.pts_num()
+    assert torch.equal(npc2.cloud_pos_tensor(), npc.cloud_pos_tensor())
+    assert torch.equal(npc2.get_geo_feats(), npc.get_geo_feats()) and torch.equal(npc2.get_col_feats(), npc.get_col_feats())
+    assert npc2.input_pos() == npc.input_pos() and npc2.input_rgb() == npc.input_rgb()
+    q = torch.from_numpy(z['knn_pts']).to(DEV)
+    for a, b in zip(npc.find_neighbors_faiss(q, step='query'), npc2.find_neighbors_faiss(q, step='query')):
+        assert torch.equal(a, b)
+    decoders.load_state_dict(ck['decoder_state_dict'])

@@ -138,3 +138,29 @@ def test_add_neural_points_bookkeeping_with_stubbed_kernels(monkeypatch):
     import pytest
     with pytest.raises(AssertionError):                                        # the reference's shape assertion (:209)
         npc.add_neural_points(ro, rd, gd, col, dynamic_radius=r_add)
+
+
+def test_checkpoint_format_matches_reference_logger(tmp_path):
+    """Keys, key order, value types and file name of `Logger.log` equal what the unmodified reference Logger wrote for the
+    same arguments in the build container (src/utils/Logger.py:20-44; the type table below was printed by that run)."""
+    import types
+    from point_slam_b200.src.utils.Logger import Logger, CKPT_KEYS
+    ref_types = {'geo_feats': 'Tensor', 'col_feats': 'Tensor', 'cloud_pos': 'list', 'pts_num': 'int', 'input_pos': 'list',
+                 'input_rgb': 'list', 'decoder_state_dict': 'OrderedDict', 'gt_c2w_list': 'Tensor', 'estimate_c2w_list': 'Tensor',
+                 'keyframe_list': 'list', 'keyframe_dict': 'list', 'selected_keyframes': 'dict', 'idx': 'int',
+                 'exposure_feat_all': 'Tensor'}
+    dec = torch.nn.Linear(2, 2)
+    m = types.SimpleNamespace(verbose=False, ckptsdir=str(tmp_path), gt_c2w_list=torch.zeros(3, 4, 4),
+                              estimate_c2w_list=torch.zeros(3, 4, 4), decoders=dec)
+    buf = torch.randn(16, 32)                                   # capacity buffer; the npc hands out a view of 5 rows
+    npc = types.SimpleNamespace(get_geo_feats=lambda: buf[:5], get_col_feats=lambda: buf[:5] * 2, cloud_pos=lambda: [[0., 0., 0.]] * 5,
+                                pts_num=lambda: 5, input_pos=lambda: [[0., 0., 0.]], input_rgb=lambda: [[1., 2., 3.]])
+    path = Logger(None, None, m).log(7, [], [0], {}, npc, exposure_feat=[torch.zeros(1, 8)] * 2)
+    assert os.path.basename(path) == '00007.tar' and os.path.exists(path)
+    ck = torch.load(path, weights_only=False)
+    assert list(ck.keys()) == list(ref_types.keys()) == list(CKPT_KEYS)
+    assert {k: type(v).__name__ for k, v in ck.items()} == ref_types
+    assert torch.equal(ck['geo_feats'], buf[:5]) and ck['geo_feats'].untyped_storage().nbytes() == 5 * 32 * 4   # exact size
+    assert ck['exposure_feat_all'].shape == (2, 1, 8)
+    path = Logger(None, None, m).log(8, [], [0], {}, npc)
+    assert torch.load(path, weights_only=False)['exposure_feat_all'] is None
