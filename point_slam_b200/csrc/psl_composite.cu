@@ -129,26 +129,60 @@ __global__ void k_pair_keys(const int* __restrict__ I, const float* __restrict__
     vals[p] = (unsigned)p;
 }
 
+// One warp per window of 32 consecutive sorted pairs: segment heads are found with one coalesced key load + ballot, then
+// each head's segment is summed cooperatively (lane = channel) in PAIR ORDER -- the order the previous one-warp-per-pair
+// version used, so results are bit-identical -- with the (key, pair) entries of up to 32 pairs fetched by one coalesced load
+// and the gathers of four pairs in flight before their (ordered) accumulation.
 __global__ void k_scatter_segments(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
                                    long long n_pairs, unsigned n_points, const float* __restrict__ wn,
                                    const float* __restrict__ d_cg, const float* __restrict__ d_colpair,
                                    const float* __restrict__ d_cc, float* __restrict__ d_geo, float* __restrict__ d_col) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_pairs; p += nwarps) {
-        const unsigned key = keys[p];
-        if (key >= n_points) continue;
-        if (p > 0 && keys[p - 1] == key) continue;
-        float ag = 0.f, ac = 0.f;
-        for (long long j = p; j < n_pairs && keys[j] == key; ++j) {
-            const unsigned pid = vals[j];
-            const float w = wn[pid];
-            const long long m = pid >> 3;
-            if (d_geo) ag += w * d_cg[m * 32 + lane];
-            if (d_col) ac += d_colpair ? d_colpair[(long long)pid * 32 + lane] : w * d_cc[m * 32 + lane];
+    const long long n_win = (n_pairs + 31) >> 5;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_win; w += nwarps) {
+        const long long p0 = w << 5, pj = p0 + lane;
+        const unsigned k = pj < n_pairs ? keys[pj] : 0xffffffffu;
+        unsigned kprev = __shfl_up_sync(0xffffffffu, k, 1);
+        if (lane == 0) kprev = p0 > 0 ? keys[p0 - 1] : 0xffffffffu;
+        unsigned heads = __ballot_sync(0xffffffffu, pj < n_pairs && k < n_points && (pj == 0 || kprev != k));
+        while (heads) {
+            const int h = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const unsigned key = __shfl_sync(0xffffffffu, k, h);
+            float ag = 0.f, ac = 0.f;
+            for (long long j0 = p0 + h;; j0 += 32) {
+                const long long j = j0 + lane;
+                const bool in = j < n_pairs;
+                const unsigned kj = in ? keys[j] : 0xffffffffu;
+                const unsigned pid_l = in ? vals[j] : 0u;
+                const unsigned same = __ballot_sync(0xffffffffu, kj == key);
+                const int cnt = same == 0xffffffffu ? 32 : __ffs(~same) - 1;      // leading pairs of this segment
+                const float w_l = lane < cnt ? wn[pid_l] : 0.f;
+                for (int t0 = 0; t0 < cnt; t0 += 4) {
+                    float wv[4], g[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u < cnt ? t0 + u : t0;                   // (clamped lanes are not accumulated)
+                        const unsigned pid = __shfl_sync(0xffffffffu, pid_l, t);
+                        wv[u] = __shfl_sync(0xffffffffu, w_l, t);
+                        const long long m = pid >> 3;
+                        g[u] = d_geo ? d_cg[m * 32 + lane] : 0.f;
+                        c[u] = d_col ? (d_colpair ? d_colpair[(long long)pid * 32 + lane] : d_cc[m * 32 + lane]) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (t0 + u < cnt) {
+                            if (d_geo) ag = fmaf(wv[u], g[u], ag);
+                            if (d_col) ac = d_colpair ? __fadd_rn(ac, c[u]) : fmaf(wv[u], c[u], ac);
+                        }
+                    }
+                }
+                if (cnt < 32) break;
+            }
+            if (d_geo) d_geo[(long long)key * 32 + lane] = ag;
+            if (d_col) d_col[(long long)key * 32 + lane] = ac;
         }
-        if (d_geo) d_geo[(long long)key * 32 + lane] = ag;
-        if (d_col) d_col[(long long)key * 32 + lane] = ac;
     }
 }
 
@@ -242,7 +276,7 @@ extern "C" int psl_feat_scatter_mapped(const int32_t* I, int64_t m, const int32_
     int bits = 1;
     while ((1ll << bits) <= n_points) ++bits;
     PSL_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, k_in, k_out, v_in, v_out, (int)np, 0, bits, st));
-    long long blocks = (np * 32 + 255) / 256;
+    long long blocks = (((np + 31) / 32) * 32 + 255) / 256;      // one warp per window of 32 sorted pairs
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     k_scatter_segments<<<(unsigned)blocks, 256, 0, st>>>(k_out, v_out, np, (unsigned)n_points, wn, d_cg, d_colpair, d_cc,

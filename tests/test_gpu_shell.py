@@ -360,6 +360,48 @@ def test_feat_scatter_mapped_equals_dense_scatter_on_selected_rows():
     assert float((dg.double() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
 
 
+def test_feat_scatter_long_segments_sum_in_pair_order():
+    """Few points, many pairs per point (segments of several hundred pairs: multi-chunk path of k_scatter_segments): every row is
+    the fused-multiply-add chain over its pairs in ascending pair order -- checked bit for bit against a float64-emulated fma
+    chain on the host -- for the per-pair colour gradient (rel-pos on), the per-sample one (rel-pos off) and the geometry one."""
+    L, lib = _lib()
+    g = torch.Generator(device=DEV).manual_seed(33)
+    N, M = 37, 3000
+    I = torch.randint(0, N, (M, 8), device=DEV, generator=g, dtype=torch.int32)
+    I[torch.rand(M, 8, device=DEV, generator=g) < 0.1] = -1
+    I[:, 0] = 5                                              # one very long segment (3000 pairs)
+    wn = torch.rand(M, 8, device=DEV, generator=g)
+    wn[I < 0] = 0.0
+    wn[torch.rand(M, 8, device=DEV, generator=g) < 0.05] = 0.0
+    d_cg = torch.randn(M, 32, device=DEV, generator=g)
+    d_cc = torch.randn(M, 32, device=DEV, generator=g)
+    d_colpair = torch.randn(M, 8, 32, device=DEV, generator=g)
+    ws_bytes = lib.psl_feat_scatter_ws_bytes(M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    out = {}
+    for name, pair, cc in (('rel', d_colpair, None), ('norel', None, d_cc)):
+        dg = torch.zeros(N, 32, device=DEV); dc = torch.zeros(N, 32, device=DEV)
+        L.check(lib.psl_feat_scatter(L.ptr(I), M, N, L.ptr(wn), L.ptr(d_cg), L.ptr(pair), L.ptr(cc), L.ptr(dg), L.ptr(dc), L.ptr(ws),
+                                     ws_bytes, L.stream()), 'psl_feat_scatter')
+        out[name] = (dg.cpu().numpy(), dc.cpu().numpy())
+    assert np.array_equal(out['rel'][0], out['norel'][0])
+    Ih, wh = I.cpu().numpy().reshape(-1), wn.cpu().numpy().reshape(-1)
+    cg, cc_h, cp = d_cg.cpu().numpy(), d_cc.cpu().numpy(), d_colpair.cpu().numpy().reshape(-1, 32)
+    fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+    for row in (5, 0, 11, 36):
+        ag = np.zeros(32, np.float32); ac_rel = np.zeros(32, np.float32); ac_no = np.zeros(32, np.float32)
+        pairs = np.nonzero((Ih == row) & (wh != 0))[0]
+        assert pairs.size > 64
+        for pid in pairs:                                    # ascending pair id == the stable sort's order inside a segment
+            w = np.full(32, wh[pid], np.float32)
+            ag = fma(w, cg[pid >> 3], ag)
+            ac_rel = (ac_rel + cp[pid]).astype(np.float32)
+            ac_no = fma(w, cc_h[pid >> 3], ac_no)
+        assert np.array_equal(out['rel'][0][row], ag), row
+        assert np.array_equal(out['rel'][1][row], ac_rel), row
+        assert np.array_equal(out['norel'][1][row], ac_no), row
+
+
 def test_shell_entry_points_reject_bad_arguments():
     L, lib = _lib()
     d = torch.zeros(9000, device=DEV); o = torch.zeros(9000, device=DEV); m = torch.zeros(9000, dtype=torch.uint8, device=DEV)
