@@ -254,27 +254,38 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 const int excl = incl - (int)rng.y;
-                for (int t0 = 0; t0 < total; t0 += 32) {
-                    const int t = t0 + lane;
-                    int c = 0;
+                // candidates of these 32 cells, 4 x 32 at a time: the four point loads are issued before any of them is
+                // consumed (one L2 round trip per 128 candidates instead of one per 32)
+                for (int t0 = 0; t0 < total; t0 += 128) {
+                    if (nstaged > KNN_CAP - 128) flush();
+                    float4 pt[4];
 #pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int v = __shfl_sync(0xffffffffu, incl, c + step - 1);
-                        if (v <= t) c += step;
+                    for (int u = 0; u < 4; ++u) {
+                        pt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t0 + 32 * u < total) {                      // warp-uniform
+                            const int t = t0 + 32 * u + lane;
+                            int c = 0;
+#pragma unroll
+                            for (int step = 16; step > 0; step >>= 1) {
+                                const int v = __shfl_sync(0xffffffffu, incl, c + step - 1);
+                                if (v <= t) c += step;
+                            }
+                            c = c > 31 ? 31 : c;
+                            const int cstart = __shfl_sync(0xffffffffu, (int)rng.x, c);
+                            const int cexcl = __shfl_sync(0xffffffffu, excl, c);
+                            if (t < total) pt[u] = __ldg(g.pts + cstart + (t - cexcl));
+                        }
                     }
-                    c = c > 31 ? 31 : c;
-                    const int cstart = __shfl_sync(0xffffffffu, (int)rng.x, c);
-                    const int cexcl = __shfl_sync(0xffffffffu, excl, c);
-                    bool keep = false;
-                    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t < total) {
-                        pt = __ldg(g.pts + cstart + (t - cexcl));
-                        keep = pt.x >= bx0 && pt.x <= bx1 && pt.y >= by0 && pt.y <= by1 && pt.z >= bz0 && pt.z <= bz1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (t0 + 32 * u < total) {
+                            const bool keep = (t0 + 32 * u + lane < total) && pt[u].x >= bx0 && pt[u].x <= bx1 && pt[u].y >= by0 &&
+                                              pt[u].y <= by1 && pt[u].z >= bz0 && pt[u].z <= bz1;
+                            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                            if (keep) s_cand[nstaged + __popc(bal & ((1u << lane) - 1u))] = pt[u];
+                            nstaged += __popc(bal);
+                        }
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                    if (keep) s_cand[nstaged + __popc(bal & ((1u << lane) - 1u))] = pt;
-                    nstaged += __popc(bal);
-                    if (nstaged > KNN_CAP - 32) flush();
                 }
             }
             if (nstaged > 0) flush();

@@ -19,7 +19,8 @@ __device__ __forceinline__ uint2 grid_lookup(const GridDev& g, uint64_t key) {
     uint32_t slot = (uint32_t)mix64(key) & g.mask;
     for (;;) {
         const uint64_t k = __ldg(g.tkeys + slot);
-        if (k == key) return __ldg(g.tvals + slot);
+        const uint2 v = __ldg(g.tvals + slot);       // fetched with the key (one round trip when the first probe hits)
+        if (k == key) return v;
         if (k == kEmptyKey) return make_uint2(0u, 0u);
         slot = (slot + 1) & g.mask;
     }
