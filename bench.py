@@ -426,11 +426,11 @@ class CpuScene:
         return samples
 
 
-CPU_TRACK_ITERS, CPU_MAP_ITERS = 20, 8            # bounded sample of the frame step for the CPU legs (~10 s on the host cores)
+CPU_TRACK_ITERS, CPU_MAP_ITERS = 40, 16           # bounded sample of the frame step for the CPU legs (~10 s on the host cores)
 
 
 def cpu_baseline_sample(n_points):
-    """Bounded sample of the same workload on the host cores: 20 tracking iterations (1500 rays) + 8 mapping iterations
+    """Bounded sample of the same workload on the host cores: 40 tracking iterations (1500 rays) + 16 mapping iterations
     (5000 rays, colour stage), after untimed warm-ups that also pick the faster of {all, 32} torch threads."""
     sc = CpuScene(n_points, 3)
     times = {}
