@@ -32,37 +32,68 @@ __global__ void k_add_valid(const float* __restrict__ depth, int n, int* __restr
     if (i < n) valid[i] = depth[i] > 0.f ? 1 : 0;
 }
 
-// one thread per ray: is there NO indexed point with D < r^2 around the surface point?  (neural_point.py:118-121,199-213)
-__global__ void k_add_probe(GridDev g, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                            const float* __restrict__ depth, int n, const int* __restrict__ valid_rank,
-                            const double* __restrict__ r2, double r2_scalar, int* __restrict__ keep) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float dep = depth[i];
-    if (!(dep > 0.f)) { keep[i] = 0; return; }
-    if (g.n == 0) { keep[i] = 1; return; }                 // untrained index: every valid ray is kept (:116)
-    const float qx = __fadd_rn(rays_o[3 * i], __fmul_rn(rays_d[3 * i], dep));
-    const float qy = __fadd_rn(rays_o[3 * i + 1], __fmul_rn(rays_d[3 * i + 1], dep));
-    const float qz = __fadd_rn(rays_o[3 * i + 2], __fmul_rn(rays_d[3 * i + 2], dep));
-    const double rr = r2 ? r2[valid_rank[i]] : r2_scalar;  // dynamic radii are given for the depth > 0 rays only
-    const float tlt = thr_lt_of(rr);
-    const float rf = sqrtf(fmaxf(tlt, 0.f)) * 1.001f + 1e-5f;
-    const int cx0 = cell_coord(qx - rf, g.inv_cell), cy0 = cell_coord(qy - rf, g.inv_cell), cz0 = cell_coord(qz - rf, g.inv_cell);
-    const int cx1 = cell_coord(qx + rf, g.inv_cell), cy1 = cell_coord(qy + rf, g.inv_cell), cz1 = cell_coord(qz + rf, g.inv_cell);
-    const long long ncell = (long long)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) * (cz1 - cz0 + 1);
-    bool found = false;
-    if (cx1 >= cx0 && cy1 >= cy0 && cz1 >= cz0 && ncell <= (1ll << 15)) {     // NaN / absurd radius: no neighbours
-        for (int cz = cz0; cz <= cz1 && !found; ++cz)
-            for (int cy = cy0; cy <= cy1 && !found; ++cy)
-                for (int cx = cx0; cx <= cx1 && !found; ++cx) {
-                    const uint2 rng = grid_lookup(g, cell_key(cx, cy, cz));
-                    for (uint32_t j = 0; j < rng.y; ++j) {
-                        const float4 c = __ldg(g.pts + rng.x + j);
-                        if (sqdist_canonical(c.x, c.y, c.z, qx, qy, qz) < tlt) { found = true; break; }
-                    }
+// one WARP per ray: is there NO indexed point with D < r^2 around the surface point?  (neural_point.py:118-121,199-213)
+// Lanes look up the cells of the query ball (<= 27 for r <= cell), the cell ranges are flattened with a warp prefix sum and
+// the candidate points are tested 32 at a time (coalesced float4 loads, canonical fp32 distance); the warp leaves at the first
+// hit.  (The first version walked the cells with one thread per ray: 83-94 us for 6000 rays at 4.8 % issue utilisation,
+// profiles/r01g_summary.md.)
+__global__ void __launch_bounds__(256) k_add_probe(GridDev g, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                   const float* __restrict__ depth, int n, const int* __restrict__ valid_rank,
+                                                   const double* __restrict__ r2, double r2_scalar, int* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+        const float dep = depth[i];
+        if (!(dep > 0.f)) { if (lane == 0) keep[i] = 0; continue; }
+        if (g.n == 0) { if (lane == 0) keep[i] = 1; continue; }       // untrained index: every valid ray is kept (:116)
+        const float qx = __fadd_rn(rays_o[3 * i], __fmul_rn(rays_d[3 * i], dep));
+        const float qy = __fadd_rn(rays_o[3 * i + 1], __fmul_rn(rays_d[3 * i + 1], dep));
+        const float qz = __fadd_rn(rays_o[3 * i + 2], __fmul_rn(rays_d[3 * i + 2], dep));
+        const double rr = r2 ? r2[valid_rank[i]] : r2_scalar;        // dynamic radii are given for the depth > 0 rays only
+        const float tlt = thr_lt_of(rr);
+        const float rf = sqrtf(fmaxf(tlt, 0.f)) * 1.001f + 1e-5f;
+        const int cx0 = cell_coord(qx - rf, g.inv_cell), cy0 = cell_coord(qy - rf, g.inv_cell), cz0 = cell_coord(qz - rf, g.inv_cell);
+        const int cx1 = cell_coord(qx + rf, g.inv_cell), cy1 = cell_coord(qy + rf, g.inv_cell), cz1 = cell_coord(qz + rf, g.inv_cell);
+        const int nx = cx1 - cx0 + 1, ny = cy1 - cy0 + 1, nz = cz1 - cz0 + 1;
+        long long ncell = (long long)nx * ny * nz;
+        if (nx <= 0 || ny <= 0 || nz <= 0 || ncell > (1ll << 15)) ncell = 0;   // NaN / absurd radius: no neighbours
+        bool found = false;
+        for (long long base = 0; base < ncell && !found; base += 32) {
+            const long long ci = base + lane;
+            uint2 rng = make_uint2(0u, 0u);
+            if (ci < ncell) {
+                const int ix = (int)(ci % nx), iy = (int)((ci / nx) % ny), iz = (int)(ci / ((long long)nx * ny));
+                rng = grid_lookup(g, cell_key(cx0 + ix, cy0 + iy, cz0 + iz));
+            }
+            int incl = (int)rng.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - (int)rng.y;
+            for (int t0 = 0; t0 < total && !found; t0 += 32) {
+                const int t = t0 + lane;
+                int c = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, c + step - 1);
+                    if (v <= t) c += step;
                 }
+                c = c > 31 ? 31 : c;
+                const int cstart = __shfl_sync(0xffffffffu, (int)rng.x, c);
+                const int cexcl = __shfl_sync(0xffffffffu, excl, c);
+                bool hit = false;
+                if (t < total) {
+                    const float4 p = __ldg(g.pts + cstart + (t - cexcl));
+                    hit = sqdist_canonical(p.x, p.y, p.z, qx, qy, qz) < tlt;
+                }
+                found = __any_sync(0xffffffffu, hit);
+            }
+        }
+        if (lane == 0) keep[i] = found ? 0 : 1;
     }
-    keep[i] = found ? 0 : 1;
 }
 
 struct AddEmitArgs {
@@ -209,7 +240,12 @@ extern "C" int psl_add_points(const psl_grid* grid_host, const float* rays_o, co
     TimingScope ts(T_MAP, st, 5);
     k_add_valid<<<nblkm(n, 256), 256, 0, st>>>(gt_depth, (int)n, valid);
     PSL_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w, cub_bytes, valid, valid_rank, (int)n, st));
-    k_add_probe<<<nblkm(n, 128), 128, 0, st>>>(g, rays_o, rays_d, gt_depth, (int)n, valid_rank, r2_valid, r2_scalar, keep);
+    {
+        long long blocks = (n * 32 + 255) / 256;                   // one warp per ray
+        const long long cap = (long long)sm_count() * 8;
+        k_add_probe<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, rays_o, rays_d, gt_depth, (int)n, valid_rank, r2_valid,
+                                                                            r2_scalar, keep);
+    }
     PSL_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w, cub_bytes, keep, keep_rank, (int)n, st));
     AddEmitArgs a{};
     a.rays_o = rays_o; a.rays_d = rays_d; a.depth = gt_depth; a.color = gt_color;
