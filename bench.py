@@ -429,18 +429,26 @@ class CpuScene:
 CPU_TRACK_ITERS, CPU_MAP_ITERS = 40, 16           # bounded sample of the frame step for the CPU legs (~10 s on the host cores)
 
 
+def pick_threads(sc):
+    """The faster of {all host threads, 32} torch threads on a small untimed step each (tiny ATen ops oversubscribe a
+    128-thread box: 32 threads were 7x faster there).  Uses frames 0 and 1 of `sc`; independent of --warmup."""
+    times = {}
+    for k, th in enumerate([os.cpu_count()] + ([32] if os.cpu_count() > 32 else [])):
+        torch.set_num_threads(th)
+        sc.step(k, 1, 1, 500)                              # first touch (allocator, thread pool)
+        t0 = time.perf_counter()
+        sc.step(k, 2, 1, 500)
+        times[th] = time.perf_counter() - t0
+    threads = min(times, key=times.get)
+    torch.set_num_threads(threads)
+    return threads
+
+
 def cpu_baseline_sample(n_points):
     """Bounded sample of the same workload on the host cores: 40 tracking iterations (1500 rays) + 16 mapping iterations
     (5000 rays, colour stage), after untimed warm-ups that also pick the faster of {all, 32} torch threads."""
     sc = CpuScene(n_points, 3)
-    times = {}
-    for k, th in enumerate([os.cpu_count()] + ([32] if os.cpu_count() > 32 else [])):
-        torch.set_num_threads(th)
-        t0 = time.perf_counter()
-        sc.step(k, 1, 1, 500)
-        times[th] = time.perf_counter() - t0
-    threads = min(times, key=times.get)
-    torch.set_num_threads(threads)
+    threads = pick_threads(sc)
     t0 = time.perf_counter()
     n = sc.step(2, CPU_TRACK_ITERS, CPU_MAP_ITERS, MAP_PIX)
     dt = time.perf_counter() - t0
@@ -455,25 +463,15 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     if rank != 0:
         return
-    sc = CpuScene(args.points, args.steps + args.warmup)
-    # thread count: all host threads unless the second warm-up step shows that 32 are faster (tiny ops oversubscribe)
-    threads = os.cpu_count()
-    torch.set_num_threads(threads)
-    times = {}
+    sc = CpuScene(args.points, args.steps + args.warmup + 2)
+    threads = pick_threads(sc)
     for k in range(args.warmup):
-        if k == 1 and os.cpu_count() > 32:
-            torch.set_num_threads(32)
-        t0 = time.perf_counter()
-        sc.step(k, 1, 1, 500)
-        times[torch.get_num_threads()] = time.perf_counter() - t0
-    if len(times) == 2:
-        threads = min(times, key=times.get)
-    torch.set_num_threads(threads)
+        sc.step(2 + k, 1, 1, 500)
     t0 = time.perf_counter()
     samples = 0
     r_track, r_map = max(CPU_TRACK_ITERS // 2, 1), max(CPU_MAP_ITERS // 2, 1)
     for k in range(args.steps):
-        samples += sc.step(args.warmup + k, r_track, r_map, MAP_PIX)
+        samples += sc.step(2 + args.warmup + k, r_track, r_map, MAP_PIX)
     dt = time.perf_counter() - t0
     v = samples / dt
     sample = (f'per step: {r_track} tracking iterations x {TRACK_PIX} rays + {r_map} mapping iterations x {MAP_PIX} rays (colour stage), '
