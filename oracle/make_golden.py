@@ -78,7 +78,7 @@ def grads_dict(model, prefix='grad.'):
 
 
 def run_case(name, scene, config, overrides, stage, is_tracker, R, S=None, seed=7, zero_depth_frac=0.0,
-             loss_kind='mapper', use_cam_tensor=False, exposure=None, pretrained=True):
+             loss_kind='mapper', use_cam_tensor=False, exposure=None, pretrained=True, write_params=True):
     ov = dict(overrides or {})
     if S is not None:
         ov['rendering.N_surface'] = S
@@ -109,7 +109,7 @@ def run_case(name, scene, config, overrides, stage, is_tracker, R, S=None, seed=
                 encode_rel_pos=bool(cfg['model']['encode_rel_pos_in_col']),
                 encode_exposure=bool(cfg['model']['encode_exposure']),
                 sample_near_pcl=bool(cfg['rendering']['sample_near_pcl']),
-                near_end=cfg['rendering']['near_end'], seed=seed)
+                near_end=cfg['rendering']['near_end'], seed=seed, nn_weighting=cfg['pointcloud']['nn_weighting'])
     if dyn is not None:
         save['dynamic_r_query'] = dyn.numpy()
 
@@ -179,7 +179,8 @@ def run_case(name, scene, config, overrides, stage, is_tracker, R, S=None, seed=
     save.update(grads_dict(model))
     np.savez_compressed(os.path.join(OUT, f'case_{name}.npz'), **save)
     pkey = f"decoders_{'exposure' if cfg['model']['encode_exposure'] else 'base'}.npz"
-    np.savez_compressed(os.path.join(OUT, pkey), **{k: v.numpy() for k, v in P.items()})
+    if write_params:
+        np.savez_compressed(os.path.join(OUT, pkey), **{k: v.numpy() for k, v in P.items()})
     print(f'{name:28s} R={R} S={S} loss={loss.item():.6f} valid={int(valid.sum())}/{R} '
           f'depth[{depth.min().item():.3f},{depth.max().item():.3f}]')
 
@@ -233,6 +234,15 @@ def run_aux(scene):
     print('aux: add kept', int(k1), int(k2), 'near_pcl invalid', int(inv.sum()), '/ 96')
 
 
+def run_expo(scene):
+    rep = 'configs/Replica/room0.yaml'
+    ov = {'pointcloud.nn_weighting': 'expo'}
+    # mapper only: with a pose gradient the reference itself raises (decoder.py:156-157 zeroes the output of torch.exp in
+    # place, which ExpBackward needs) -- 'expo' cannot be trained through the tracker path in the reference
+    run_case('expo_mapper', scene, rep, ov, 'color', False, 96, seed=17, write_params=False)
+    run_case('expo_mapper_geometry', scene, rep, ov, 'geometry', False, 96, seed=18, write_params=False)
+
+
 def run_frustum():
     """Mapper.get_mask_from_c2w (src/Mapper.py:120-168) of the unmodified reference on a whole-room cloud: two poses of a
     quarter-size camera, sensor depth with zero-depth holes, the shipped frustum_edge (-4) and a positive one."""
@@ -262,8 +272,11 @@ def run_frustum():
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == 'frustum':        # only the newest fixture (the others stay byte-identical)
+    if len(sys.argv) > 1 and sys.argv[1] == 'frustum':        # only that fixture (the others stay byte-identical)
         run_frustum()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'expo':           # nn_weighting='expo' (decoder.py:154-156; unused by the shipped configs)
+        run_expo(make_scene())
         return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -285,6 +298,7 @@ def main():
              use_cam_tensor=True, exposure='feat')
     run_case('exposure_mapper_raw', scene, scn, None, 'color', False, 96, seed=15)
     run_aux(scene)
+    run_expo(scene)
     run_frustum()
 
 

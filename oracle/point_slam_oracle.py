@@ -223,10 +223,10 @@ def softplus100(x):
     return F.softplus(x, beta=100)
 
 
-def idw_weights(D, r2):
-    """decoder.py:152-160 -- 1/(D+1e-10), zero where D > r^2 (strict, float64 compare when
-    r^2 is float64), then L1-normalise with eps 1e-12."""
-    w = 1.0 / (D + 1e-10)
+def idw_weights(D, r2, weighting='distance'):
+    """decoder.py:152-160 -- 1/(D+1e-10) (or exp(-20 sqrt(D)) for nn_weighting='expo', :154-156), zero where D > r^2
+    (strict, float64 compare when r^2 is float64), then L1-normalise with eps 1e-12."""
+    w = 1.0 / (D + 1e-10) if weighting == 'distance' else torch.exp(-20 * torch.sqrt(D))
     w = torch.where(D.double() > r2.reshape(-1, 1), torch.zeros_like(w), w)
     return F.normalize(w, p=1, dim=1)
 
@@ -235,26 +235,26 @@ def _lin(P: Params, name: str, x):
     return F.linear(x, P[name + '.weight'], P[name + '.bias'])
 
 
-def interp_geo(P, p, D_knn, I, neighbor_num, r2, geo_feats, cloud_pos, is_tracker, rand_vec):
+def interp_geo(P, p, D_knn, I, neighbor_num, r2, geo_feats, cloud_pos, is_tracker, rand_vec, weighting='distance'):
     """MLP_geometry.get_feature_at_pos, decoder.py:130-173."""
     D = D_knn.to(p.dtype)
     if is_tracker:                                             # :143-148 (pose gradient path)
         D = torch.square(cloud_pos[I] - p.reshape(-1, 1, 3)).sum(-1)
     has_neighbors = neighbor_num > MIN_NN_NUM - 1              # :150
-    w = idw_weights(D, r2).unsqueeze(-1)
+    w = idw_weights(D, r2, weighting).unsqueeze(-1)
     c = (w * geo_feats[I]).sum(1)
     c = torch.where(has_neighbors[:, None], c, rand_vec.to(c.dtype)[None, :])   # :170-171
     return c, has_neighbors
 
 
 def interp_col(P, p, D_knn, I, neighbor_num, r2, col_feats, cloud_pos, is_tracker, rand_vec,
-               encode_rel_pos=True):
+               encode_rel_pos=True, weighting='distance'):
     """MLP_color.get_feature_at_pos, decoder.py:341-390."""
     D = D_knn.to(p.dtype)
     if is_tracker:
         D = torch.square(cloud_pos[I] - p.reshape(-1, 1, 3)).sum(-1)
     has_neighbors = neighbor_num > MIN_NN_NUM - 1
-    w = idw_weights(D, r2).unsqueeze(-1)
+    w = idw_weights(D, r2, weighting).unsqueeze(-1)
     f = col_feats[I]
     if encode_rel_pos:                                         # :373-381
         rel = cloud_pos[I] - p[:, None, :]
@@ -302,16 +302,16 @@ def col_trunk(P, p, c, exposure_mode='none', exposure_feat=None):
 
 
 def point_forward(P, p, stage, knn, r2, geo_feats, col_feats, cloud_pos, S, is_tracker,
-                  rand_geo, rand_col, encode_rel_pos=True, exposure_mode='none', exposure_feat=None):
+                  rand_geo, rand_col, encode_rel_pos=True, exposure_mode='none', exposure_feat=None, weighting='distance'):
     """POINT.forward, decoder.py:476-518 -> raw (M,4), ray_mask (R,), point_mask (M,)."""
     D, I, nnum = knn
-    c_g, has_nb = interp_geo(P, p, D, I, nnum, r2, geo_feats, cloud_pos, is_tracker, rand_geo)
+    c_g, has_nb = interp_geo(P, p, D, I, nnum, r2, geo_feats, cloud_pos, is_tracker, rand_geo, weighting)
     occ = geo_trunk(P, p, c_g)
     ray_mask = ~(has_nb.view(-1, S).sum(1) < int(S / 2 + 1))           # :200-201
     if stage == 'geometry':
         raw = torch.cat([torch.zeros(occ.shape[0], 3, dtype=occ.dtype), occ[:, None]], -1)
         return raw, ray_mask, has_nb
-    c_c, _ = interp_col(P, p, D, I, nnum, r2, col_feats, cloud_pos, is_tracker, rand_col, encode_rel_pos)
+    c_c, _ = interp_col(P, p, D, I, nnum, r2, col_feats, cloud_pos, is_tracker, rand_col, encode_rel_pos, weighting)
     rgb = col_trunk(P, p, c_c, exposure_mode, exposure_feat)
     return torch.cat([rgb, occ[:, None]], -1), ray_mask, has_nb
 
@@ -348,7 +348,7 @@ def render_batch_ray(P, rays_d, rays_o, gt_depth, stage, cloud_pos, geo_feats, c
                      rand_geo=None, rand_col=None, coef=0.1, encode_rel_pos=True,
                      exposure_mode='none', exposure_feat=None, sample_near_pcl=False,
                      near_surface=0.98, far_surface=1.02, near_end=0.3, tree=None, knn=None,
-                     z_zero_depth=None, mask_not_near=None, return_aux=False):
+                     z_zero_depth=None, mask_not_near=None, return_aux=False, weighting='distance'):
     """Renderer.render_batch_ray, src/utils/Renderer.py:77-202."""
     R = rays_o.shape[0]
     z_vals, nz = sample_z_vals(gt_depth.detach(), S, near_surface, far_surface, near_end, z_zero_depth)
@@ -363,7 +363,7 @@ def render_batch_ray(P, rays_d, rays_o, gt_depth, stage, cloud_pos, geo_feats, c
         rand_col = torch.zeros(C_DIM)
     raw, ray_mask, point_mask = point_forward(P, p, stage, knn, r2, geo_feats, col_feats, cloud_pos, S,
                                               is_tracker, rand_geo, rand_col, encode_rel_pos,
-                                              exposure_mode, exposure_feat)
+                                              exposure_mode, exposure_feat, weighting)
     raw = mask_occupancy(raw, point_mask).reshape(R, S, 4)
     depth, var, color, w = composite(raw, z_vals, coef)
     near_mask = torch.ones(R, dtype=torch.bool)

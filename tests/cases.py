@@ -11,6 +11,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 INTR = synth.TUM_INTRINSICS
 CASES = ['mapper_color', 'mapper_geometry', 'tracker_color', 'fixed_radius_zero_depth', 'tum_near_pcl',
          'tum_tracker', 's32_color', 'exposure_tracker', 'exposure_mapper_raw']
+# nn_weighting='expo' (decoder.py:154-156): unused by the shipped configs and not differentiable w.r.t. the pose in the reference
+# (its in-place masking breaks ExpBackward), so only mapper cases exist.  Oracle pinned; GPU: see tests/test_gpu_parity.py
+EXPO_CASES = ['expo_mapper', 'expo_mapper_geometry']
 
 
 def load_scene(dtype=torch.float32, device='cpu'):
@@ -34,6 +37,7 @@ def load_case(name):
     for k in ('is_tracker', 'use_dynamic_radius', 'encode_rel_pos', 'encode_exposure', 'sample_near_pcl'):
         c[k] = bool(c[k])
     c['S'] = int(c['S'])
+    c['nn_weighting'] = str(c['nn_weighting']) if 'nn_weighting' in c else 'distance'
     c['name'] = name
     # ScanNet config uses a wider sampling interval (configs/ScanNet/scannet.yaml:33-34)
     c['near_surface'], c['far_surface'] = (0.96, 1.04) if c['encode_exposure'] else (0.98, 1.02)
@@ -83,7 +87,8 @@ def run_oracle(c, dtype=torch.float32, tree=None):
         rand_geo=torch.from_numpy(c['rand_geo']), rand_col=torch.from_numpy(c['rand_col']),
         encode_rel_pos=c['encode_rel_pos'], exposure_mode=exposure_mode(c), exposure_feat=ef,
         sample_near_pcl=c['sample_near_pcl'], near_surface=c['near_surface'], far_surface=c['far_surface'],
-        near_end=float(c['near_end']), knn=knn, z_zero_depth=zz, mask_not_near=mnn, return_aux=True)
+        near_end=float(c['near_end']), knn=knn, z_zero_depth=zz, mask_not_near=mnn, return_aux=True,
+        weighting=c['nn_weighting'])
     if c['loss_kind'] == 'tracker':
         loss = O.tracker_loss(depth, var, color, gt_depth, gt_color)
     else:

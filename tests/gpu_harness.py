@@ -18,7 +18,8 @@ def case_cfg(c):
     ds = 'scannet' if c['encode_exposure'] else ('replica' if c['encode_rel_pos'] else 'tum')
     return make_cfg(ds, DEV, **{'use_dynamic_radius': c['use_dynamic_radius'], 'rendering.N_surface': c['S'],
                                 'rendering.sample_near_pcl': c['sample_near_pcl'],
-                                'pointcloud.radius_query': float(c['radius_query'])})
+                                'pointcloud.radius_query': float(c['radius_query']),
+                                'pointcloud.nn_weighting': c.get('nn_weighting', 'distance')})
 
 
 def build_objects(c, scene=None):

@@ -103,7 +103,13 @@ def test_composite_matches_reference_vectors():
     assert C.rel_err(raw.grad.cpu(), r2.grad) < 1e-5
 
 
-@pytest.mark.parametrize('name', C.CASES)
+_EXPO = [pytest.param(n, marks=pytest.mark.xfail(strict=False, reason="nn_weighting='expo' (unused by every shipped config) runs on the FFMA "
+                                                  'kernels only; the cases were frozen after the last GPU session of the round, so this '
+                                                  'branch has not been run on hardware yet'))
+         for n in C.EXPO_CASES]
+
+
+@pytest.mark.parametrize('name', C.CASES + _EXPO)
 def test_render_case_against_oracle(name, oracle_cache):
     from tests.gpu_harness import run_case_gpu
     c, o32, o64 = _oracles(name, oracle_cache)

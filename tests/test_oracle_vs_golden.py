@@ -10,7 +10,7 @@ from tests import cases as C
 TOL = 2e-5      # oracle and reference are both fp32 torch on the CPU: only op-fusion order differs
 
 
-@pytest.mark.parametrize('name', C.CASES)
+@pytest.mark.parametrize('name', C.CASES + C.EXPO_CASES)
 def test_case_forward_and_grads(name):
     c = C.load_case(name)
     o = C.run_oracle(c)
@@ -35,7 +35,7 @@ def test_case_forward_and_grads(name):
         if gk in c:
             assert C.rel_err(g, c[gk]) < 2e-4, k
             n_checked += 1
-    assert n_checked >= 10
+    assert n_checked >= (10 if c['stage'] == 'color' or name in C.CASES else 5)
 
 
 def test_aux_knn_contract():
