@@ -8,6 +8,7 @@ from oracle import point_slam_oracle as O
 from point_slam_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INTR = synth.TUM_INTRINSICS
 CASES = ['mapper_color', 'mapper_geometry', 'tracker_color', 'fixed_radius_zero_depth', 'tum_near_pcl',
          'tum_tracker', 's32_color', 'exposure_tracker', 'exposure_mapper_raw']
