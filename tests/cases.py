@@ -13,7 +13,7 @@ INTR = synth.TUM_INTRINSICS
 CASES = ['mapper_color', 'mapper_geometry', 'tracker_color', 'fixed_radius_zero_depth', 'tum_near_pcl',
          'tum_tracker', 's32_color', 'exposure_tracker', 'exposure_mapper_raw']
 # nn_weighting='expo' (decoder.py:154-156): unused by the shipped configs and not differentiable w.r.t. the pose in the reference
-# (its in-place masking breaks ExpBackward), so only mapper cases exist.  Oracle pinned; GPU: see tests/test_gpu_parity.py
+# (its in-place masking breaks ExpBackward), so only mapper cases exist (FFMA kernels on the GPU, incl. their weight-gradient phases)
 EXPO_CASES = ['expo_mapper', 'expo_mapper_geometry']
 
 

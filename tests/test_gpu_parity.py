@@ -103,12 +103,8 @@ def test_composite_matches_reference_vectors():
     assert C.rel_err(raw.grad.cpu(), r2.grad) < 1e-5
 
 
-@pytest.mark.parametrize('name', C.CASES)
+@pytest.mark.parametrize('name', C.CASES + C.EXPO_CASES)
 def test_render_case_against_oracle(name, oracle_cache):
-    _check_render_case(name, oracle_cache)
-
-
-def _check_render_case(name, oracle_cache):
     from tests.gpu_harness import run_case_gpu
     c, o32, o64 = _oracles(name, oracle_cache)
     got = run_case_gpu(c)
@@ -194,19 +190,3 @@ def test_add_neural_points_and_sample_near_pcl():
     assert npc.get_geo_feats().shape[0] == npc.pts_num() == npc.index_ntotal()
     assert np.array_equal(np.asarray(npc.input_pos(), np.float32), z['add_input_pos'])
 
-
-@pytest.mark.xfail(strict=False, reason="nn_weighting='expo' (unused by every shipped config) takes the FFMA colour kernels incl. their "
-                                        'weight-gradient phases; the cases were frozen after the last GPU session of the round, so the '
-                                        'branch has not been run on hardware yet')
-@pytest.mark.parametrize('name', C.EXPO_CASES)
-def test_expo_weighting_case_in_subprocess(name):
-    """Same checks as test_render_case_against_oracle, in a child process: a fault in a not-yet-exercised branch must not take the
-    CUDA context of the rest of the suite with it."""
-    import subprocess
-    import sys
-    code = ('import sys; sys.path.insert(0, %r)\n'
-            'from tests import test_gpu_parity as T\n'
-            'T._check_render_case(%r, {})\n'
-            'print("EXPO-OK")\n') % (C.ROOT, name)
-    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and 'EXPO-OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
