@@ -164,3 +164,55 @@ def test_checkpoint_format_matches_reference_logger(tmp_path):
     assert ck['exposure_feat_all'].shape == (2, 1, 8)
     path = Logger(None, None, m).log(8, [], [0], {}, npc)
     assert torch.load(path, weights_only=False)['exposure_feat_all'] is None
+
+
+def test_replica_append_points_matches_source_cloud(monkeypatch):
+    """parallel.make_delta / apply_delta on two real NeuralPointCloud objects (kernels stubbed by the oracle as above): after the
+    mapping rank added points and changed feature rows, the replica brought up to date through `append_points` /
+    `update_*_feats` holds bit-identical positions and features, and both keep valid row-prefix views of their buffers."""
+    from oracle import point_slam_oracle as O
+    from point_slam_b200 import ops, parallel as PL
+    from point_slam_b200.src.neural_point import NeuralPointCloud
+
+    def fake_build(self, cloud_pos):
+        self._cloud = cloud_pos.detach().clone().float().reshape(-1, 3)
+        self.n = self._cloud.shape[0]
+        return self
+
+    def fake_add_points(grid, ro, rd, dep, col, new_pos, radius, dynamic_radius=None, n_add=3, fixed_interval=False,
+                        near_surface=0.98, far_surface=1.02):
+        m = dep > 0
+        keep, pts = O.add_points(getattr(grid, '_cloud', None), ro, rd, dep, radius_add=radius, N_add=n_add,
+                                 near_surface=near_surface, far_surface=far_surface)
+        new_pos[:pts.shape[0]] = pts
+        k = int(keep.sum())
+        in_pos, in_rgb = torch.zeros(dep.shape[0], 3), torch.zeros(dep.shape[0], 3)
+        in_pos[:k] = (ro[m] + rd[m] * dep[m][:, None])[keep]
+        return torch.tensor([int(m.sum()), k], dtype=torch.int32), in_pos, in_rgb
+
+    monkeypatch.setattr(ops.SpatialHash, 'build', fake_build)
+    monkeypatch.setattr(ops, 'add_points', fake_add_points)
+    z = np.load(C.GOLDEN + '/aux.npz')
+    ro, rd, gd = (torch.from_numpy(z[k]) for k in ('add_rays_o', 'add_rays_d', 'add_depth'))
+    dec = torch.nn.Module()
+    dec.color_decoder = torch.nn.Linear(3, 2)
+    src, rep = NeuralPointCloud(make_cfg('replica', 'cpu')), NeuralPointCloud(make_cfg('replica', 'cpu'))
+    torch.manual_seed(4)
+    src.add_neural_points(ro[:200], rd[:200], gd[:200], torch.zeros(200, 3))           # first batch: everything valid is kept
+    d0 = PL.make_delta(src, dec, 0, None)
+    PL.apply_delta(rep, dec, d0)
+    for step in range(3):                                                              # grow past the first capacity
+        n_before = src.pts_num()
+        lo = 200 + 60 * step
+        src.add_neural_points(ro[lo:lo + 60] + 5.0 * (step + 1), rd[lo:lo + 60], gd[lo:lo + 60], torch.zeros(60, 3))
+        upd = torch.tensor([1, 5, n_before - 1])
+        src.update_geo_feats(torch.full((3, 32), float(step)), upd)
+        src.update_col_feats(torch.full((3, 32), -float(step)), upd)
+        PL.apply_delta(rep, dec, PL.make_delta(src, dec, n_before, upd))
+        assert rep.pts_num() == src.pts_num() == rep.index_ntotal() == src.index_ntotal() > n_before
+        assert torch.equal(rep.cloud_pos_tensor(), src.cloud_pos_tensor())
+        assert torch.equal(rep.get_geo_feats(), src.get_geo_feats()) and torch.equal(rep.get_col_feats(), src.get_col_feats())
+        for npc in (src, rep):
+            assert npc.get_geo_feats().data_ptr() == npc._geo_buf.data_ptr() and npc._geo_buf.shape[0] >= npc.pts_num()
+            assert npc.cloud_pos_tensor().data_ptr() == npc._pos_buf.data_ptr()
+    assert rep.cloud_pos() == src.cloud_pos()
