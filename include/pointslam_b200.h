@@ -230,6 +230,14 @@ int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const floa
                      float* save /* NULL, or the psl_decode_fwd save buffer (FFMA backward) */,
                      float* tsave /* NULL, or psl_tc_save_floats() floats (tensor-core backward) */, psl_stream_t stream);
 
+/* EXPERIMENT, same contract as psl_color_fwd_tc: 16 worker warps (4 threads per sample row, 16-column epilogue chunks) instead
+ * of 8 -- csrc/psl_color_tc_w16.cu.  Not on the default path (PSL_W16=1 selects it in ops.py); written after the last GPU
+ * session of round 1 and not yet run on hardware. */
+int psl_color_fwd_tc_w16(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
+                         const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                         const float* rand_col, const float* exposure_affine, float* raw, float* save, float* tsave,
+                         psl_stream_t stream);
+
 /* tensor-core training path of the colour branch: psl_color_fwd_tc(tsave) -> psl_color_bwd_tc (data gradients; the
  * geometry branch, the IDW-weight gradient and d_pos are finished by psl_decode_bwd(stage = GEOMETRY, dwn_extra, dpos_extra)). */
 size_t psl_tc_fold_offset_floats(void);

@@ -1,6 +1,10 @@
 """tcgen05 building blocks (psl_tc.cuh): 3xTF32 GEMM with fp32 TMEM accumulation must match fp32/fp64 matmul."""
+import os
+
 import pytest
 import torch
+
+from tests import cases as C
 
 pytestmark = pytest.mark.gpu
 
@@ -96,3 +100,38 @@ def test_tensor_core_backward_data_path(name):
     tol('geo feature grad', got['grad_geo'], o32['grad_geo'], o64['grad_geo'])
     tol('col feature grad', got['grad_col'], o32['grad_col'], o64['grad_col'])
     assert not got['grad_params']
+
+
+@pytest.mark.skipif(os.environ.get('PSL_EXPERIMENTAL', '0') != '1',
+                    reason='experiment kernel (16 worker warps, csrc/psl_color_tc_w16.cu): written after the last GPU session of round 1; '
+                           'run with PSL_EXPERIMENTAL=1')
+@pytest.mark.parametrize('name', ['mapper_color', 'tracker_color', 'tum_tracker', 's32_color', 'exposure_tracker', 'fixed_radius_zero_depth'])
+def test_w16_forward_experiment(name):
+    """The 16-worker-warp forward performs the same arithmetic per element as the production kernel (only the assignment of
+    columns to threads differs), so inference output, training outputs and every gradient computed from its saved activations
+    must be BIT-IDENTICAL.  Runs in a child process: a fault in an unproven kernel must not take this suite's CUDA context."""
+    import subprocess
+    import sys
+    code = '''
+import sys, torch
+sys.path.insert(0, %r)
+from point_slam_b200 import ops
+from tests import cases as C
+from tests.gpu_harness import run_case_gpu
+c = C.load_case(%r)
+out = {}
+for w16 in (False, True):
+    ops.USE_W16_FORWARD = w16
+    out[w16] = (run_case_gpu(c), run_case_gpu(c, freeze_decoders=True))
+torch.cuda.synchronize()
+for a, b in zip(out[False], out[True]):
+    for k in ('depth', 'var', 'color', 'loss', 'grad_geo', 'grad_col'):
+        assert torch.equal(a[k], b[k]), k
+    for k in a['grad_params']:
+        assert torch.equal(a['grad_params'][k], b['grad_params'][k]), k
+    if 'grad_cam' in a:
+        assert torch.equal(a['grad_cam'], b['grad_cam'])
+print('W16-OK')
+''' % (C.ROOT, name)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'W16-OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
