@@ -492,11 +492,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_color_bwd_tc(Args a, long long n_ti
                                 da = dx[jj] * cs - dx[10 + jj] * sn;
                             }
                             gx = fmaf(da, Br[jj], gx); gy = fmaf(da, Br[12 + jj], gy); gz = fmaf(da, Br[24 + jj], gz);
-                            // d Brel[c][jj] += (2 pi rel_c) d arg : warp reduction, lane (c*10 + jj) keeps the sum
-                            const float t0 = warp_sum(da * rx), t1 = warp_sum(da * ry), t2 = warp_sum(da * rz);
-                            if (lane == jj) brel_acc += t0;
-                            if (lane == 10 + jj) brel_acc += t1;
-                            if (lane == 20 + jj) brel_acc += t2;
+                            // d Brel[c][jj] += (2 pi rel_c) d arg : warp reduction, lane (c*10 + jj) keeps the sum.  Only the
+                            // weight-gradient pass reads it (k_wgrad_finalize): skipped for the tracker (240 reductions per tile)
+                            if (a.want_wgrad) {
+                                const float t0 = warp_sum(da * rx), t1 = warp_sum(da * ry), t2 = warp_sum(da * rz);
+                                if (lane == jj) brel_acc += t0;
+                                if (lane == 10 + jj) brel_acc += t1;
+                                if (lane == 20 + jj) brel_acc += t2;
+                            }
                         }
                         dpx -= kTwoPi * gx; dpy -= kTwoPi * gy; dpz -= kTwoPi * gz;
                     }
