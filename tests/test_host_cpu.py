@@ -216,3 +216,27 @@ def test_replica_append_points_matches_source_cloud(monkeypatch):
             assert npc.get_geo_feats().data_ptr() == npc._geo_buf.data_ptr() and npc._geo_buf.shape[0] >= npc.pts_num()
             assert npc.cloud_pos_tensor().data_ptr() == npc._pos_buf.data_ptr()
     assert rep.cloud_pos() == src.cloud_pos()
+
+
+def test_entry_points_reject_null_arguments_without_a_gpu():
+    """Error behaviour of the C ABI (include/pointslam_b200.h: 0 or a negative code, message through psl_last_error, never a
+    crash): NULL / malformed arguments are refused BEFORE any CUDA call, so this runs on the CPU-only build box."""
+    lib = _lib.load()
+    C_ = ctypes
+    g = _lib.Grid(None, None, None, 0, 0, 0.08, 0.0)
+    z12 = (C_.c_double * 12)()
+    assert lib.psl_add_points(None, None, None, None, None, 10, None, 0.0016, 3, 0, 0.98, 1.02, None, None, None, None, None, None, 0, None) < 0
+    assert b'grid' in lib.psl_last_error()
+    assert lib.psl_add_points(C_.byref(g), None, None, None, None, 10, None, 0.0016, 3, 0, 0.98, 1.02, None, None, None, None, None, None, 0,
+                              None) < 0
+    assert b'NULL' in lib.psl_last_error()
+    assert lib.psl_frustum_select(None, 10, z12, 500.0, 500.0, 320.0, 240.0, None, 480, 640, -4, None, None, None, None, 0, None) < 0
+    assert b'NULL' in lib.psl_last_error()
+    assert lib.psl_frustum_select(None, 10, None, 500.0, 500.0, 320.0, 240.0, None, 480, 640, -4, None, None, None, None, 0, None) < 0
+    bad = _lib.Grid(None, None, None, 3, 5, 0.08, 0.0)                      # capacity not a power of two
+    assert lib.psl_knn_query(C_.byref(bad), None, 0, None, 0.0064, 1, None, None, None, None) < 0
+    assert b'capacity' in lib.psl_last_error()
+    assert lib.psl_feat_scatter(None, 8, 100, None, None, None, None, None, None, None, 0, None) < 0
+    assert lib.psl_composite_fwd(None, None, None, 4, 5, 0.1, None, None, None, None, None) < 0
+    assert lib.psl_color_fwd_tc_w16(None, None, None, 4, None, None, None, None, None, None, None, None, None, None, None, None) < 0
+    assert lib.psl_add_points_ws_bytes(6000) > 4 * 6000 * 4 and lib.psl_frustum_select_ws_bytes(500000) > 500000 * 5
