@@ -252,6 +252,14 @@ int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob, const flo
                      float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
                      psl_stream_t stream);
 
+/* EXPERIMENT, same contract as psl_color_bwd_tc: 16 worker warps, the half-0-only steps of the production kernel spread over
+ * four column quarters -- csrc/psl_color_bwd_tc_w16.cu.  Not on the default path (PSL_W16=1), not yet run on hardware. */
+int psl_color_bwd_tc_w16(const psl_decode_cfg* cfg, const float* bwd_blob, const float* pos, int64_t m, const int32_t* I,
+                         const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                         const float* exposure_affine, const float* raw, const float* d_raw, const float* tsave, float* tbwd,
+                         float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
+                         psl_stream_t stream);
+
 /* weight gradients of the colour branch (GEMMs over the sample index) from the buffers left by psl_color_fwd_tc(tsave) and
  * psl_color_bwd_tc(want_wgrad = 1); only the c_* entries of `grads_host` are written.  ws: psl_wgrad_tc_ws_floats(m). */
 size_t psl_wgrad_tc_ws_floats(int64_t m);

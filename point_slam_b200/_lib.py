@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 # PSL_LIB: load another build of the same sources (A/B experiments, e.g. one compiled with -DPSL_PRECISE_TRIG)
 LIB_PATH = os.environ.get('PSL_LIB') or os.path.join(_HERE, 'libpointslam_b200.so')
-SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_tc_w16.cu', 'psl_color_bwd_tc.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu', 'psl_map.cu']
-HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_grid.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh', 'psl_color_tc.cuh']
+SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_tc_w16.cu', 'psl_color_bwd_tc.cu', 'psl_color_bwd_tc_w16.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu', 'psl_map.cu']
+HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_grid.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh', 'psl_color_tc.cuh', 'psl_color_bwd_tc.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
 
@@ -103,6 +103,8 @@ _SIGS = {
     'psl_frustum_select_ws_bytes': (_sz, [_i64]),
     'psl_frustum_select': (C.c_int, [_vp, _i64, C.POINTER(_f64), _f64, _f64, _f64, _f64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                      _sz, _vp]),
+    'psl_color_bwd_tc_w16': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp]),
     'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)

@@ -8,7 +8,7 @@
 //
 // Status: written after the last GPU session of round 1 -- compiles for sm_100a, NOT yet run on hardware.  Every mbarrier wait
 // of this kernel carries a clock watchdog (trap after ~2 s) so that a choreography mistake ends the launch with an error
-// instead of hanging the device.  tests/test_gpu_tc.py::test_w16_forward_experiment runs it only when PSL_EXPERIMENTAL=1.
+// instead of hanging the device.  tests/test_gpu_tc.py::test_w16_experiment runs it only when PSL_EXPERIMENTAL=1.
 #include "psl_color_tc.cuh"
 
 namespace psl {
@@ -18,20 +18,7 @@ using namespace ctc;
 
 constexpr int NWORK16 = 512, NTHR16 = 576;      // warps 0-15 workers, 16 bulk-copy producer, 17 TMEM allocator + MMA issuer
 
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (uint32_t n = 1; !mbar_try(bar, parity); ++n)
-        if ((n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
-}
+using tc::mbar_wait_wd;
 __device__ __forceinline__ void worker_signal16(uint64_t* a_ready) {
     tc::tmem_st_wait();
     tc::fence_before_sync();

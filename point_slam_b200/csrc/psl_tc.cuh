@@ -160,6 +160,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// watchdog variant for kernels that have not run on hardware yet: traps after ~2 s instead of spinning forever, so that a
+// barrier-choreography mistake ends the launch with an error and cannot hang the device
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (uint32_t n = 1; !mbar_try(bar, parity); ++n)
+        if ((n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+}
 // global -> shared 1-D bulk copy (bytes multiple of 16, both addresses 16 B aligned); completes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

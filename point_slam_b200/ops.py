@@ -180,6 +180,7 @@ USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour br
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
 USE_W16_FORWARD = os.environ.get('PSL_W16', '0') == '1'       # EXPERIMENT: 16-worker-warp colour forward (psl_color_tc_w16.cu)
+USE_W16_BACKWARD = os.environ.get('PSL_W16', '0') == '1'      # EXPERIMENT: 16-worker-warp colour backward (psl_color_bwd_tc_w16.cu)
 OVERLAP_BRANCHES = os.environ.get('PSL_OVERLAP', '1') != '0'  # geometry kernel on a forked stream next to the colour kernel
 _SIDE = {}
 
@@ -348,10 +349,11 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
         if side is not None:
             side.wait_stream(main)
-        L.check(lib.psl_color_bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                                     L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
-                                     L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
-                                     int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')
+        bwd_tc = lib.psl_color_bwd_tc_w16 if USE_W16_BACKWARD else lib.psl_color_bwd_tc
+        L.check(bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                       L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
+                       L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
+                       int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')
         if side is not None:
             with torch.cuda.stream(side):
                 geometry_backward(None, None)

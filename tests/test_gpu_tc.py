@@ -103,13 +103,12 @@ def test_tensor_core_backward_data_path(name):
 
 
 @pytest.mark.skipif(os.environ.get('PSL_EXPERIMENTAL', '0') != '1',
-                    reason='experiment kernel (16 worker warps, csrc/psl_color_tc_w16.cu): written after the last GPU session of round 1; '
+                    reason='experiment kernels (16 worker warps, csrc/psl_color_tc_w16.cu, psl_color_bwd_tc_w16.cu): written after the last GPU session of round 1; '
                            'run with PSL_EXPERIMENTAL=1')
 @pytest.mark.parametrize('name', ['mapper_color', 'tracker_color', 'tum_tracker', 's32_color', 'exposure_tracker', 'fixed_radius_zero_depth'])
-def test_w16_forward_experiment(name):
-    """The 16-worker-warp forward performs the same arithmetic per element as the production kernel (only the assignment of
-    columns to threads differs), so inference output, training outputs and every gradient computed from its saved activations
-    must be BIT-IDENTICAL.  Runs in a child process: a fault in an unproven kernel must not take this suite's CUDA context."""
+def test_w16_experiment(name):
+    """The 16-worker-warp forward and backward perform the same arithmetic per element, in the same order, as the production
+    kernels (only the assignment of columns / steps to threads differs), so outputs and every gradient must be BIT-IDENTICAL.  Runs in a child process: a fault in an unproven kernel must not take this suite's CUDA context."""
     import subprocess
     import sys
     code = '''
@@ -120,17 +119,20 @@ from tests import cases as C
 from tests.gpu_harness import run_case_gpu
 c = C.load_case(%r)
 out = {}
-for w16 in (False, True):
-    ops.USE_W16_FORWARD = w16
-    out[w16] = (run_case_gpu(c), run_case_gpu(c, freeze_decoders=True))
+for key, (fwd16, bwd16) in (('prod', (False, False)), ('fwd', (True, False)), ('bwd', (False, True)), ('both', (True, True))):
+    ops.USE_W16_FORWARD, ops.USE_W16_BACKWARD = fwd16, bwd16
+    out[key] = (run_case_gpu(c), run_case_gpu(c, freeze_decoders=True))
 torch.cuda.synchronize()
-for a, b in zip(out[False], out[True]):
-    for k in ('depth', 'var', 'color', 'loss', 'grad_geo', 'grad_col'):
-        assert torch.equal(a[k], b[k]), k
-    for k in a['grad_params']:
-        assert torch.equal(a['grad_params'][k], b['grad_params'][k]), k
-    if 'grad_cam' in a:
-        assert torch.equal(a['grad_cam'], b['grad_cam'])
+for key in ('fwd', 'bwd', 'both'):                     # 'fwd' / 'bwd' alone localise a mismatch to one kernel
+    for a, b in zip(out['prod'], out[key]):
+        for k in ('depth', 'var', 'color', 'loss', 'grad_geo', 'grad_col'):
+            assert torch.equal(a[k], b[k]), (key, k)
+        for k in a['grad_params']:
+            assert torch.equal(a['grad_params'][k], b['grad_params'][k]), (key, k)
+        if 'grad_cam' in a:
+            assert torch.equal(a['grad_cam'], b['grad_cam']), key
+        if 'grad_exposure_feat' in a:
+            assert torch.equal(a['grad_exposure_feat'], b['grad_exposure_feat']), key
 print('W16-OK')
 ''' % (C.ROOT, name)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
