@@ -74,7 +74,11 @@ __global__ void k_hash_tails(const uint64_t* __restrict__ keys, int n, const uin
 // query
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_WARPS = 8;
-constexpr int KNN_CAP = 512;
+#ifndef PSL_KNN_CAP
+#define PSL_KNN_CAP 512        // candidates staged per warp before a merge; -DPSL_KNN_CAP=256 halves the shared memory per CTA
+#endif                         // (82 -> 49 KB: 3 CTAs per SM instead of 2) at the price of more merges -- A/B with PSL_LIB
+constexpr int KNN_CAP = PSL_KNN_CAP;
+static_assert(KNN_CAP >= 256 && KNN_CAP % 128 == 0, "KNN_CAP: multiple of 128, at least 256");
 constexpr unsigned long long KEY_INF = ~0ull;
 
 __device__ __forceinline__ void list_insert(unsigned long long (&k)[8], unsigned long long x) {
