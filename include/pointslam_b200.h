@@ -328,6 +328,9 @@ int psl_frustum_select(const float* cloud_pos, int64_t n, const double* w2c_host
 
 /* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
 int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
+/* same self-test with 16-bit operand planes (kind::f16: hi = f16, lo = bf16, formats mixed per MMA): mode 2 = TS (A in TMEM, two k per
+   column), mode 3 = SS; scratch N*K floats */
+int psl_tc_gemm_test_h(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, int variant, psl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,7 @@ _SIGS = {
     'psl_color_bwd_tc_w16': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp]),
     'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'psl_tc_gemm_test_h': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)
 

@@ -42,6 +42,44 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // (MN-major tf32 operands without swizzle were tried for the weight-gradient GEMM and return zeros on sm_100a; the
 // wgrad kernel therefore transposes while staging and keeps every operand K-major.)
 
+// ---- 16-bit operand planes (kind::f16): a = hi + lo with hi = f16(a) (11 significand bits, saturating) and lo = bf16(a - hi)
+// (the residual is exact in fp32; bf16 keeps its 8 leading bits, so hi + lo carries ~19 bits and the three products
+// hi*hi + lo*hi + hi*lo reproduce a*w to ~2^-20 relative).  Two K-consecutive values share one 32-bit word, even k in the low half.
+// all-f16 variant: lo = f16(a - hi) (goes subnormal below |a| ~ 0.1: absolute error <= 3e-8 there)
+__device__ __forceinline__ void split_h2_f16(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+    float f0, f1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f0), "=f"(f1) : "r"(hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(a1 - f1), "f"(a0 - f0));
+}
+__device__ __forceinline__ void split_h2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+    float f0, f1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f0), "=f"(f1) : "r"(hi));
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(a1 - f1), "f"(a0 - f0));
+}
+// canonical K-major, non-swizzled layout of a 16-bit (R x K) operand, in 2-byte elements: 8x16-byte core matrices (8 rows x 8 k)
+__host__ __device__ __forceinline__ uint32_t canon_off_h(int r, int k, int R) {
+    return (uint32_t)(((k >> 3) * (R >> 3) + (r >> 3)) * 64 + (r & 7) * 8 + (k & 7));
+}
+// instruction descriptor of kind::f16: D = f32, A / B formats chosen independently (0 = f16, 1 = bf16), both K-major
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1;
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]^T     (single thread issues)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
