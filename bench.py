@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- Point-SLAM render hot path on B200: ray-samples/sec (render + kNN + MLP), frames/sec.
 
-    python bench.py --gpus 1 --steps 10 --warmup 3            # CUDA path (this repo)
-    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host cores (CPU oracle port)
+    python bench.py --gpus 1 --steps 5 --warmup 3                    # CUDA path (this repo), workload C2
+    python bench.py --config c3                                      # other BASELINE.json configs: c1, c3, c4
+    python bench.py --impl reference --steps 3 --warmup 1            # the reference algorithm on the host cores (CPU oracle port)
 
-One STEP = the hot-path work the reference does for one Replica-config frame:
-40 tracking iterations x 1500 rays (render fwd + loss + bwd to the 7-d pose + Adam) and the per-frame share of
-mapping, 300/5 = 60 iterations x 5000 rays over the current frame + 4 keyframes (first 40 % geometry stage, then colour;
-bwd to the frustum-selected feature slices and the colour decoder + Adam), S = 5 samples per ray, against a
-replicated synthetic 500k-point neural point cloud, 640x480 synthetic RGB-D frames (point_slam_b200/synth.py).
-`value` = ray-samples through render fwd+bwd per second with the frame already in HBM; `e2e` = the same step fed
-from pinned HOST memory (frame colour/depth/radius map H2D, pose + loss D2H inside the timed region).
-Multi-GPU (`--gpus N`, torchrun): one independent scene per GPU (BASELINE config C5, the reference's SLURM array),
-no data-path collective -> weak scaling.
+Workloads (BASELINE.json `configs`; shapes from the reference's YAML files):
+  c2 (default, the configuration `metric` is quoted on): one STEP = the hot-path work of one Replica-config frame:
+     40 tracking iterations x 1500 rays (render fwd + loss + bwd to the 7-d pose + Adam, Tracker.py:89-186), then the map update
+     of a mapped frame -- add_neural_points on 6000 + 1000 pixels (Mapper.py:306-331), frustum feature selection
+     (Mapper.py:345) -- and the per-frame share of mapping, 300/5 = 60 iterations x 5000 rays over the current frame + 4
+     keyframes (25 geometry-stage then 35 colour-stage iterations: `joint_iter <= int(n * 0.4)`, Mapper.py:420; bwd to the
+     frustum-selected feature rows and the colour decoder + Adam), S = 5, 500k-point cloud, 640x480 synthetic RGB-D frames.
+     The map update runs EVERY step (the reference maps every 5th frame), so its cost is over-weighted five-fold.
+  c4: TUM-fr1_desk-like tracking only: 200 iterations x 5000 rays, noisy depth + 5 % holes, rel-pos encoding off (tum.yaml).
+  c1 / c3: forward render of one ray batch (1000 rays x 5 samples vs 50k points; 5000 rays x 32 samples vs 2M points).
+`value` = ray-samples per second with the inputs already in HBM; `e2e` = the same step fed from pinned HOST memory (frame /
+ray batch H2D, pose + loss / rendered pixels D2H inside the timed region).
+Multi-GPU (`--gpus N`, torchrun): one independent scene per GPU (BASELINE config C5, the reference's SLURM array), no
+data-path collective -> weak scaling; `--share-map` adds the design's one collective (NCCL broadcast of the map delta from
+rank 0 after its map update, point_slam_b200/parallel.py) to every step.
 """
 import argparse
 import json
@@ -33,14 +40,41 @@ from point_slam_b200.default_config import make_cfg                  # noqa: E40
 from point_slam_b200 import iteration as IT                          # noqa: E402
 
 INTR = synth.TUM_INTRINSICS
-S = 5
-TRACK_ITERS, TRACK_PIX = 40, 1500            # configs/Replica/replica.yaml:7-8
-MAP_ITERS, MAP_PIX = 60, 5000                # 300 iterations every 5th frame (replica.yaml:15,17; point_slam.yaml:42)
-GEO_ITERS = int(MAP_ITERS * 0.4)             # mapping.geo_iter_ratio (point_slam.yaml:41)
 N_KEYFRAMES = 4
-ALGO_BYTES_FWD = 2144 + 49.0 / S             # gathered bytes per sample, colour stage forward
-ALGO_BYTES_BWD = 2144 + 2048 + 49.0 / S      # + feature-gradient writes before dedup
-FLOP_FWD = 397894                            # SURVEY.md section 8d (encode_rel_pos_in_col=True)
+FLOP_FWD = {True: 397894, False: 225382}     # forward FLOP per sample with / without the rel-pos neighbour MLP
+TC_MAC = {True: 182956, False: 96700}        # colour-branch MACs per sample on the tensor cores (trunk + neighbour MLP / trunk)
+
+CONFIGS = {
+    # mode, dataset cfg, points, S, (track iters, rays), (map iters, rays), edge, noise, holes
+    'c2': dict(mode='slam', dataset='replica', points=500000, S=5, track=(40, 1500), map=(60, 5000), edge=100, noise=False, holes=0.0,
+               name='C2 Replica-office0-like frame'),
+    'c4': dict(mode='track', dataset='tum', points=500000, S=5, track=(200, 5000), map=None, edge=20, noise=True, holes=0.05,
+               name='C4 TUM-fr1_desk-like tracking only'),
+    'c1': dict(mode='render', dataset='replica', points=50000, S=5, rays=1000, name='C1 single-batch render'),
+    'c3': dict(mode='render', dataset='replica', points=2000000, S=32, rays=5000, name='C3 2M-point cloud, MLP-decode roofline'),
+}
+
+
+def geo_iters(n_map):
+    """Geometry-stage iterations of a mapping call of n_map iterations: joint_iter <= int(n * geo_iter_ratio), Mapper.py:420."""
+    return min(int(n_map * 0.4) + 1, n_map)
+
+
+def workload_config(name, points):
+    """The `config` object of the JSON line -- identical for the CUDA arm and the reference arm."""
+    c = CONFIGS[name]
+    if c['mode'] == 'render':
+        return {'workload': f"{c['name']}: {c['rays']} rays x {c['S']} samples, {points} pts, forward render (kNN + decode + composite)",
+                'points': points, 'rays': c['rays'], 'S': c['S'], 'parallelism': 'scene-per-gpu'}
+    w = f"{c['name']}: {c['track'][0]} track it x {c['track'][1]} rays"
+    mix = {'track_iters': c['track'][0], 'track_rays': c['track'][1]}
+    if c['map']:
+        g = geo_iters(c['map'][0])
+        w += (f" + map update (add_neural_points 6000+1000 px, frustum selection) + {c['map'][0]} map it x {c['map'][1]} rays "
+              f"({g} geometry-stage, {c['map'][0] - g} colour-stage)")
+        mix.update({'map_iters': c['map'][0], 'map_rays': c['map'][1], 'geometry_stage_iters': g})
+    w += f", S={c['S']}, {points} pts, 640x480"
+    return {'workload': w, 'points': points, 'iteration_mix': mix, 'parallelism': 'scene-per-gpu'}
 
 
 def load_decoder_state():
@@ -48,13 +82,13 @@ def load_decoder_state():
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def make_frames(n, seed):
+def make_frames(n, seed, noise=False, holes=0.0):
     poses = synth.trajectory(n, seed=seed)
     frames = []
     for k in range(n):
-        depth, color = synth.make_frame(poses[k], INTR)
-        _, rq = synth.sobel_radius_map(color)
-        frames.append(dict(c2w=poses[k], depth=depth, color=color, dyn_r_query=rq))
+        depth, color = synth.make_frame(poses[k], INTR, noise=noise, holes=holes, seed=k)
+        r_add, rq = synth.sobel_radius_map(color)
+        frames.append(dict(c2w=poses[k], depth=depth, color=color, dyn_r_query=rq, dyn_r_add=r_add))
     return frames
 
 
@@ -103,124 +137,214 @@ class Clocks:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def build_decoders(cfg, device):
+    from point_slam_b200.src.conv_onet import config as model_config
+    torch.manual_seed(1219)
+    decoders = model_config.get_model(cfg)
+    sd = load_decoder_state()
+    emb = sd.pop('color_decoder.embedder._B')
+    decoders.load_state_dict(sd, strict=True)
+    decoders.color_decoder.embedder._B = emb
+    return decoders.to(device)
+
+
+def build_cloud(cfg, device, n_points, seed, reserve=None):
+    from point_slam_b200.src.neural_point import NeuralPointCloud
+    cloud = synth.make_cloud(n_points, seed=seed)
+    gf, cf = synth.make_features(n_points, seed=seed)
+    npc = NeuralPointCloud(cfg)
+    npc._cloud_pos = torch.from_numpy(cloud)
+    npc._pts_num = n_points
+    npc.geo_feats = torch.from_numpy(gf).to(device)
+    npc.col_feats = torch.from_numpy(cf).to(device)
+    if reserve:
+        npc.reserve(reserve)
+    npc.index.add(npc._pos)
+    return npc
+
+
 # ---------------------------------------------------------------------------------------------------------------------
-# CUDA arm
+# CUDA arm, tracking / mapping workloads (c2, c4)
 # ---------------------------------------------------------------------------------------------------------------------
 class GpuScene:
-    def __init__(self, rank, device, n_points, n_frames):
-        from point_slam_b200.src.conv_onet import config as model_config
-        from point_slam_b200.src.neural_point import NeuralPointCloud
+    def __init__(self, rank, device, wl, n_points, n_frames, share_map=False, dist=None):
         from point_slam_b200.src.utils.Renderer import Renderer
+        from point_slam_b200 import graphed as G, ops
         import types
-        self.device = device
-        self.cfg = make_cfg('replica', device)
-        torch.manual_seed(1219)
-        self.decoders = model_config.get_model(self.cfg)
-        sd = load_decoder_state()
-        emb = sd.pop('color_decoder.embedder._B')
-        self.decoders.load_state_dict(sd, strict=True)
-        self.decoders.color_decoder.embedder._B = emb
-        self.decoders = self.decoders.to(device)
-        cloud = synth.make_cloud(n_points, seed=1219 + rank)
-        gf, cf = synth.make_features(n_points, seed=1219 + rank)
-        self.npc = NeuralPointCloud(self.cfg)
-        self.npc._cloud_pos = torch.from_numpy(cloud)
-        self.npc._pts_num = n_points
-        self.npc.geo_feats = torch.from_numpy(gf).to(device)
-        self.npc.col_feats = torch.from_numpy(cf).to(device)
-        self.npc.index.add(self.npc._pos)
+        self.device, self.wl, self.rank, self.dist, self.share_map = device, wl, rank, dist, share_map
+        self.S = wl['S']
+        self.cfg = make_cfg(wl['dataset'], device)
+        self.decoders = build_decoders(self.cfg, device)
+        seed = 1219 + (0 if share_map else rank)
+        # capacity for everything the timed steps may append (<= 7000 pixels x 3 points per step): no re-allocation, so the
+        # captured iteration graphs stay valid while the cloud grows
+        self.npc = build_cloud(self.cfg, device, n_points, seed, reserve=n_points + (n_frames + 2) * 21000 + 4096)
         self.renderer = Renderer(self.cfg, None, types.SimpleNamespace(**{k: INTR[k] for k in ('H', 'W', 'fx', 'fy', 'cx', 'cy')}))
         self.renderer.sigmoid_coefficient = 0.1
-        self.frames_host = make_frames(n_frames + N_KEYFRAMES, seed=1219 + rank)
+        self.frames_host = make_frames(n_frames + N_KEYFRAMES, seed=seed, noise=wl['noise'], holes=wl['holes'])
         self.rng = np.random.default_rng(7 + rank)
+        self.gen = torch.Generator(device=device).manual_seed(11 + rank)
         # keyframes are resident (they were mapped earlier); incoming frames live in pinned host memory
         self.keyframes = [self._to_device(f) for f in self.frames_host[:N_KEYFRAMES]]
-        self.pinned = [{k: torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory() for k in ('color', 'depth', 'dyn_r_query')}
-                       for f in self.frames_host[N_KEYFRAMES:]]
+        keys = ('color', 'depth', 'dyn_r_query', 'dyn_r_add')
+        self.pinned = [{k: torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory() for k in keys} for f in self.frames_host[N_KEYFRAMES:]]
         self.resident = [self._to_device(f) for f in self.frames_host[N_KEYFRAMES:]]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
         self.out_host = torch.empty(8, dtype=torch.float32).pin_memory()
-        from point_slam_b200 import graphed as G, ops
+        self.r_add = torch.zeros(INTR['H'], INTR['W'], dtype=torch.float64, device=device)
         self.G, self.ops = G, ops
-        self.tracker = G.FusedTracker(self.renderer, self.npc, self.decoders, INTR, TRACK_PIX, device, edge=(100, 100))
-        self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, MAP_PIX, device)
+        tc = self.cfg['tracking']
+        self.tracker = G.FusedTracker(self.renderer, self.npc, self.decoders, INTR, wl['track'][1], device, edge=(wl['edge'], wl['edge']),
+                                      lr=tc['lr'], w_color=tc['w_color_loss'], separate_lr=tc['separate_LR'])
+        self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, wl['map'][1], device) if wl['map'] else None
+        self.map_ev = []
+        self.added = 0
+        self.channel = None
 
     def _to_device(self, f):
         d = self.device
         return dict(color=torch.from_numpy(f['color']).to(d), depth=torch.from_numpy(f['depth']).to(d),
-                    dyn_r_query=torch.from_numpy(f['dyn_r_query']).to(d),
+                    dyn_r_query=torch.from_numpy(f['dyn_r_query']).to(d), dyn_r_add=torch.from_numpy(f['dyn_r_add']).to(d),
                     c2w=torch.from_numpy(f['c2w'][:3, :4].astype(np.float32)).to(d))
 
+    def map_update(self, c2w, depth, color):
+        """The per-mapped-frame map update (Mapper.py:306-345): add_neural_points on 6000 random pixels with the per-pixel add
+        radius and on 1000 more with the small radius (the reference picks those by colour gradient on the host -- out of scope,
+        SURVEY.md section 2 row 4 -- here they are random pixels), then the frustum feature selection.  Rank 0 of a shared map
+        broadcasts the delta (new points + their feature rows) to the replicas."""
+        from point_slam_b200.src import common
+        d, npc = self.device, self.npc
+        n0 = npc.pts_num()
+        for n_pix, grad in ((6000, False), (1000, True)):
+            pix = torch.randint(0, INTR['H'] * INTR['W'], (n_pix,), device=d, generator=self.gen)
+            j, i = pix // INTR['W'], pix % INTR['W']
+            ro, rd = common.get_rays_from_uv(i.float(), j.float(), c2w, INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], d)
+            gd, gc = depth[j, i], color[j, i]
+            keep = gd > 0                                          # get_samples(depth_filter=True), common.py:173-179
+            if self.share_map and self.rank != 0:
+                continue
+            npc.add_neural_points(ro[keep], rd[keep], gd[keep], gc[keep], is_pts_grad=grad, dynamic_radius=self.r_add[j, i][keep])
+        self.added += npc.pts_num() - n0
+        return n0
+
+    def share_delta(self, n0, rows):
+        """Shared-map mode: rank 0's map delta of this frame (appended points + their feature rows, the feature rows its mapper
+        optimised, the colour decoder) reaches every replica with ONE NCCL broadcast (parallel.DeltaChannel)."""
+        from point_slam_b200 import parallel as PAR
+        if self.channel is None:
+            self.channel = PAR.DeltaChannel(self.device, PAR.n_decoder_floats(self.decoders))
+        delta = PAR.make_delta(self.npc, self.decoders, n0, rows) if self.rank == 0 else None
+        PAR.apply_delta(self.npc, self.decoders, self.channel.broadcast(delta, 0))
+
     def step(self, k, from_host, graphs=True):
-        """Process frame k: 40 tracking + 60 mapping iterations.  graphs=True: each iteration is one CUDA-graph replay of the
-        static-shape shell (point_slam_b200/graphed.py); graphs=False: the same static-shape iterations launched eagerly
-        (used for the per-kernel timing pass).  Returns the number of ray-samples rendered (fwd+bwd)."""
-        d = self.device
+        """Process frame k.  graphs=True: each iteration is one CUDA-graph replay of the static-shape shell
+        (point_slam_b200/graphed.py); graphs=False: the same iterations launched eagerly (per-kernel timing pass).
+        Returns the number of ray-samples rendered (fwd+bwd)."""
+        d, wl = self.device, self.wl
         fh = self.frames_host[N_KEYFRAMES + k]
         src = self.pinned[k] if from_host else self.resident[k]
         cam0 = cam_tensor_from_c2w(fh['c2w'], 0.01, self.rng).to(d, non_blocking=True)
         tr = self.tracker
         tr.load_frame(src['color'], src['depth'], src['dyn_r_query'], cam0)        # H2D from pinned memory in the e2e pass
-        npc, dec = self.npc, self.decoders
+        self.r_add.copy_(src['dyn_r_add'], non_blocking=True)
+        t_it, t_rays = wl['track']
         if graphs:
-            loss = tr.run(TRACK_ITERS)
+            loss = tr.run(t_it)
         else:
-            for _ in range(TRACK_ITERS):
+            for _ in range(t_it):
                 tr._iter()
             loss = tr.loss
-        cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn,
-                   c2w=torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True))
-        # frustum feature selection with the sensor-depth test, Mapper.get_mask_from_c2w (library kernel, one 4-byte D2H)
-        idx = self.ops.frustum_select(npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
-                                      INTR['cx'], INTR['cy'], edge=-4)
-        self.mapper.begin_frame(idx, [cur] + self.keyframes)
-        if graphs:
-            self.mapper.run('geometry', GEO_ITERS)
-            loss = self.mapper.run('color', MAP_ITERS - GEO_ITERS)
-        else:
-            for it in range(MAP_ITERS):
-                self.mapper._iter('geometry' if it < GEO_ITERS else 'color')
-            loss = self.mapper.loss
+        samples = t_it * t_rays * self.S
+        if self.mapper is not None:
+            m_it, m_rays = wl['map']
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c2w = torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True)
+            n0 = self.map_update(c2w, tr.depth, tr.color)
+            cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=c2w)
+            # frustum feature selection with the sensor-depth test, Mapper.get_mask_from_c2w (library kernel, one 4-byte D2H)
+            idx = self.ops.frustum_select(self.npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
+                                          INTR['cx'], INTR['cy'], edge=-4)
+            self.mapper.begin_frame(idx, [cur] + self.keyframes)
+            e1.record()
+            self.map_ev.append((e0, e1))
+            g = geo_iters(m_it)
+            if graphs:
+                self.mapper.run('geometry', g)
+                loss = self.mapper.run('color', m_it - g)
+            else:
+                for it in range(m_it):
+                    self.mapper._iter('geometry' if it < g else 'color')
+                loss = self.mapper.loss
+            rows = self.mapper.write_back()
+            if self.share_map:
+                self.share_delta(n0, rows)
+            samples += m_it * (m_rays // (1 + N_KEYFRAMES)) * (1 + N_KEYFRAMES) * self.S
         if from_host:
-            self.out_host[:7].copy_(tr.cam.detach(), non_blocking=True)
+            self.out_host[:7].copy_(tr.best_cam, non_blocking=True)
             self.out_host[7:8].copy_(loss.reshape(1), non_blocking=True)
-        return (TRACK_ITERS * TRACK_PIX + MAP_ITERS * (MAP_PIX // (1 + N_KEYFRAMES)) * (1 + N_KEYFRAMES)) * S
+        return samples
+
+    def captures(self):
+        return self.tracker.captures + (self.mapper.captures if self.mapper else 0)
 
 
-def _map_maintenance_ms(self, k, reps=5):
-    """Device time of the two per-mapped-frame map updates on frame k: frustum selection over the whole
-    cloud and add_neural_points for `pixels_adding` = 6000 rays (point_slam.yaml:61) incl. the hash rebuild.  Run after the
-    timed region: the add may grow the cloud."""
-    from point_slam_b200.src import common
-    d = self.device
-    fh = self.frames_host[N_KEYFRAMES + k]
-    fr = self.resident[k]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    sel = added = 0
-    t_sel = t_add = 0.0
-    g = torch.Generator(device=d).manual_seed(11)
-    for r in range(reps + 1):
-        pix = torch.randint(0, INTR['H'] * INTR['W'], (6000,), device=d, generator=g)
-        j, i = pix // INTR['W'], pix % INTR['W']
-        ro, rd = common.get_rays_from_uv(i.float(), j.float(), fr['c2w'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], d)
-        gd, gc = fr['depth'][j, i], fr['color'][j, i]
-        r_add = fr['dyn_r_query'][j, i] / 2.0
-        ev[0].record()
-        idx = self.ops.frustum_select(self.npc.cloud_pos_tensor(), fh['c2w'], fr['depth'], INTR['H'], INTR['W'], INTR['fx'],
-                                      INTR['fy'], INTR['cx'], INTR['cy'], edge=-4)
-        ev[1].record()
-        ev[2].record()
-        k_add = self.npc.add_neural_points(ro, rd, gd, gc, dynamic_radius=r_add[gd > 0])
-        ev[3].record()
-        torch.cuda.synchronize()
-        if r:                                           # first repetition = warm-up
-            t_sel += ev[0].elapsed_time(ev[1]); t_add += ev[2].elapsed_time(ev[3])
-            sel, added = int(idx.numel()), added + int(k_add)
-    return {'frustum_select_ms': t_sel / reps, 'selected_points': sel, 'add_neural_points_ms': t_add / reps,
-            'rays_per_add': 6000, 'locations_added_total': added, 'points': self.npc.pts_num()}
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm, forward-render workloads (c1, c3)
+# ---------------------------------------------------------------------------------------------------------------------
+class RenderScene:
+    def __init__(self, rank, device, wl, n_points, n_frames):
+        from point_slam_b200.src.utils.Renderer import Renderer
+        from point_slam_b200 import ops
+        import types
+        self.device, self.wl, self.ops = device, wl, ops
+        self.S, self.R = wl['S'], wl['rays']
+        self.cfg = make_cfg(wl['dataset'], device, **{'rendering.N_surface': self.S})
+        self.decoders = build_decoders(self.cfg, device)
+        self.npc = build_cloud(self.cfg, device, n_points, 1219 + rank)
+        self.renderer = Renderer(self.cfg, None, types.SimpleNamespace(**{k: INTR[k] for k in ('H', 'W', 'fx', 'fy', 'cx', 'cy')}))
+        self.renderer.sigmoid_coefficient = 0.1
+        frames = make_frames(n_frames, seed=1219 + rank)
+        rng = np.random.default_rng(3 + rank)
+        self.batches = []
+        for f in frames:
+            pix = rng.integers(0, INTR['H'] * INTR['W'], self.R)
+            j, i = pix // INTR['W'], pix % INTR['W']
+            o, dd = synth.pixel_rays(f['c2w'], INTR['H'], INTR['W'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'])
+            b = dict(rays_o=np.broadcast_to(o, (self.R, 3)).astype(np.float32).copy(), rays_d=dd[j, i].astype(np.float32),
+                     depth=f['depth'][j, i].copy(), r_query=f['dyn_r_query'][j, i].copy())
+            self.batches.append(b)
+        self.pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in self.batches]
+        self.resident = [{k: torch.from_numpy(v).to(device) for k, v in b.items()} for b in self.batches]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values())
+        self.out_host = torch.empty(self.R, 5, dtype=torch.float32).pin_memory()
+        self.stage = {k: torch.empty_like(v) for k, v in self.resident[0].items()}
+        self.tracker = self.mapper = None
 
+    def step(self, k, from_host, graphs=True):
+        b = self.resident[k]
+        if from_host:
+            for key, t in self.pinned[k].items():
+                self.stage[key].copy_(t, non_blocking=True)
+            b = self.stage
+        with torch.no_grad():
+            depth, unc, color, _ = self.renderer.render_batch_ray(
+                self.npc, self.decoders, b['rays_d'], b['rays_o'], self.device, 'color', gt_depth=b['depth'],
+                npc_geo_feats=self.npc.get_geo_feats(), npc_col_feats=self.npc.get_col_feats(), cloud_pos=self.npc.cloud_pos_tensor(),
+                dynamic_r_query=b['r_query'], _zero_depth=(None, None))
+        if from_host:
+            self.out_host[:, 0].copy_(depth, non_blocking=True); self.out_host[:, 1].copy_(unc, non_blocking=True)
+            self.out_host[:, 2:].copy_(color, non_blocking=True)
+        return self.R * self.S
 
-GpuScene.map_maintenance_ms = _map_maintenance_ms
+    def captures(self):
+        return 0
+
+    def knn_stats(self):
+        """Mean number of candidate points the kNN kernel stages per query (SURVEY.md section 8d asks for C-bar)."""
+        b = self.resident[0]
+        return self.ops.raymarch_knn_stats(self.npc.spatial_hash(), b['rays_o'], b['rays_d'], b['depth'], self.S,
+                                           (b['r_query'] ** 2).contiguous())
 
 
 def timed_steps(scene, steps, first, from_host, dist):
@@ -257,17 +381,28 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device(device))
     lib = _lib.load()
-    scene = GpuScene(rank, device, args.points, args.steps + args.warmup)
+    wl = CONFIGS[args.config]
+    points = args.points or wl['points']
+    render_mode = wl['mode'] == 'render'
+    n_frames = args.steps + args.warmup
+    if render_mode:
+        scene = RenderScene(rank, device, wl, points, n_frames)
+    else:
+        scene = GpuScene(rank, device, wl, points, n_frames, share_map=args.share_map and world > 1, dist=dist)
     for k in range(args.warmup):
         scene.step(k, False)
+    cap0 = scene.captures()
     clocks = Clocks(local) if rank == 0 else None
     ms, samples, per_step = timed_steps(scene, args.steps, args.warmup, False, dist)
     ms_e2e, samples_e2e, per_step_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
     clk = clocks.stop() if clocks else None
-    # per-kernel device time of one more step (CUDA events on the launching stream inside the library)
-    # (the same static-shape iterations launched eagerly: graph replays bypass the host-side event hooks)
-    # with the geometry kernels launched in-line (no stream fork): a forked kernel's slot would include the time it
-    # waits for free SMs and could be mistaken for the dominant kernel
+    recaptures = scene.captures() - cap0
+    map_ms = None
+    if getattr(scene, 'map_ev', None):
+        map_ms = float(np.mean([a.elapsed_time(b) for a, b in scene.map_ev[-2 * args.steps:]]))
+    # per-kernel device time of one more step (CUDA events on the launching stream inside the library): the same static-shape
+    # iterations launched eagerly (graph replays bypass the host-side event hooks), geometry kernels in-line (no stream fork:
+    # a forked kernel's slot would include the time it waits for free SMs and could be mistaken for the dominant kernel)
     from point_slam_b200 import ops as _ops
     l0 = lib.psl_launch_count()
     overlap, _ops.OVERLAP_BRANCHES = _ops.OVERLAP_BRANCHES, False
@@ -277,9 +412,12 @@ def run_ours(args):
     _lib.timing_enable(False)
     _ops.OVERLAP_BRANCHES = overlap
     launches = (lib.psl_launch_count() - l0) * args.steps           # kernels of this library per step x timed steps
-    maint = scene.map_maintenance_ms(args.warmup) if rank == 0 else None
+    per_rank = [ms / args.steps]
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [float(g[0]) / args.steps for g in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         s = torch.tensor([samples, samples_e2e], device=device, dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
@@ -296,20 +434,27 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bf16_peak = float(peaks.get('bf16_tflops', 1590.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    rel = bool(scene.cfg['model']['encode_rel_pos_in_col'])
+    S = wl['S']
+    bytes_fwd, bytes_bwd = 2144 + 49.0 / S, 2144 + 2048 + 49.0 / S       # SURVEY.md section 8d (gathered bytes per sample)
     tot_kernel_ms = sum(v[0] for v in prof.values())
     top = max(prof, key=lambda k: prof[k][0])
     top_ms, top_n = prof[top]
-    # samples one launch of the dominant kernel processes: the tracker launches see TRACK_PIX*S, the mapper's MAP_PIX*S
-    n_track, n_map = TRACK_ITERS * TRACK_PIX * S, MAP_ITERS * MAP_PIX * S
-    launches_of = {'wgrad_tc': MAP_ITERS - GEO_ITERS, 'color_fwd_tc': TRACK_ITERS + MAP_ITERS - GEO_ITERS,
-                   'color_bwd_tc': TRACK_ITERS + MAP_ITERS - GEO_ITERS}
-    samples_of = {'wgrad_tc': (MAP_ITERS - GEO_ITERS) * MAP_PIX * S,
-                  'color_fwd_tc': n_track + (MAP_ITERS - GEO_ITERS) * MAP_PIX * S,
-                  'color_bwd_tc': n_track + (MAP_ITERS - GEO_ITERS) * MAP_PIX * S}
-    per_launch_samples = samples_of.get(top, n_prof) / max(launches_of.get(top, prof['knn'][1]), 1)
+    # samples one launch of the dominant kernel processes (tracker launches see track_rays*S, the mapper's map_rays*S)
+    if render_mode:
+        samples_top = n_prof
+    else:
+        t_it, t_rays = wl['track']
+        m_it, m_rays = wl['map'] if wl['map'] else (0, 0)
+        col_it = m_it - geo_iters(m_it) if m_it else 0
+        per_kernel = {'wgrad_tc': col_it * m_rays * S, 'color_fwd_tc': t_it * t_rays * S + col_it * m_rays * S,
+                      'color_bwd_tc': t_it * t_rays * S + col_it * m_rays * S}
+        samples_top = per_kernel.get(top, n_prof)
+    per_launch_samples = samples_top / max(top_n, 1)
     avg_launch_s = top_ms / max(top_n, 1) * 1e-3
-    bytes_per_sample = {'decode_bwd': ALGO_BYTES_BWD, 'color_bwd_tc': ALGO_BYTES_BWD, 'wgrad_tc': ALGO_BYTES_BWD}.get(top, ALGO_BYTES_FWD)
+    bytes_per_sample = bytes_bwd if top in ('decode_bwd', 'color_bwd_tc', 'wgrad_tc') else bytes_fwd
     hbm_achieved = per_launch_samples * bytes_per_sample / avg_launch_s / 1e9
     traffic = None
     tj = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -319,42 +464,48 @@ def run_ours(args):
             traffic = t['bytes_per_sample'] * per_launch_samples          # scaled to this launch size; source in profiles/traffic.json
     hbm_view = {'achieved': hbm_achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_achieved / hbm_peak,
                 'algorithmic_bytes_per_sample': bytes_per_sample}
-    # colour branch (the tcgen05 kernels): 182 956 MAC per sample and pass, issued three times (3xTF32) on kind::tf32 MMAs
-    tc_flops = {'color_fwd_tc': 2 * 182956, 'color_bwd_tc': 2 * 182956, 'wgrad_tc': 2 * 182956}.get(top)
-    bf16_peak = float(peaks.get('bf16_tflops', 1590.0))
-    if tc_flops:
-        tf = per_launch_samples * tc_flops / avg_launch_s / 1e12
-        roof = {'bound': 'tensor', 'kernel': top, 'achieved': 3 * tf, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': 3 * tf / bf16_peak,
-                'traffic': traffic, 'peak_source': peak_src,
-                'note': 'achieved = tf32 MMA FLOP/s issued (3 MMAs per fp32-accurate product); peak = measured dense bf16 (kind::tf32 runs at half of it)',
-                'fp32_equivalent_tflops': tf, 'hbm': hbm_view}
+    if top in ('color_fwd_tc', 'color_bwd_tc', 'wgrad_tc'):
+        # ALGORITHMIC FLOPs of the launch (2 x MACs of the colour branch) over its duration against the
+        # measured dense-bf16 peak; the MMA work actually issued (error-compensated split products) is a second field
+        tf = per_launch_samples * 2 * TC_MAC[rel] / avg_launch_s / 1e12
+        roof = {'bound': 'tensor', 'kernel': top, 'achieved': tf, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': tf / bf16_peak,
+                'traffic': traffic, 'peak_source': peak_src, 'issued_mma_tflops': 3 * tf,
+                'note': 'achieved = algorithmic FLOP/s of the colour branch (no x3 for the split-operand products); issued_mma_tflops counts the 3 MMAs per fp32-accurate product',
+                'hbm': hbm_view}
     else:
         roof = {'bound': 'hbm', 'kernel': top, 'traffic': traffic, 'peak_source': peak_src, **hbm_view}
+    fwd_bwd = 1 if render_mode else 3
     roof.update({'samples_per_launch': per_launch_samples, 'avg_launch_ms': avg_launch_s * 1e3,
                  'kernel_share_of_device_time': top_ms / max(tot_kernel_ms, 1e-9),
-                 'fp32_tflops_fwd_bwd_all_kernels': 3 * FLOP_FWD * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12})
+                 'algorithmic_tflops_all_kernels': fwd_bwd * FLOP_FWD[rel] * n_prof / max(tot_kernel_ms * 1e-3, 1e-9) / 1e12})
+    cfg_out = workload_config(args.config, points)
+    cfg_out['parallelism'] = f'scene-per-gpu x{world}' + (' + NCCL map-delta broadcast from rank 0' if args.share_map and world > 1 else '')
     out = {
-        'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': value, 'unit': 'samples/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'metric': 'ray-samples/sec (render+kNN+MLP' + (' forward' if render_mode else ' fwd+bwd, frame step') + ')', 'value': value,
+        'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
         'frames_per_sec': world * args.steps / (ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'C2 Replica-office0-like frame: 40 track it x 1500 rays + 60 map it x 5000 rays, S=5, '
-                               f'{args.points} pts, 640x480; one scene per GPU', 'points': args.points,
-                   'work_per_step': 'pixel sampling + render fwd + loss + bwd + Adam (tracker pose; mapper feature rows + colour decoder); every iteration is one CUDA-graph replay of a static-shape shell of library kernels (point_slam_b200/graphed.py: FusedTracker / FusedMapper)',
-                   'l2': 'inputs larger than L2 (cloud+features 134 MB, saved activations ~290 MB / mapper iteration)',
-                   'parallelism': f'scene-per-gpu x{world}'},
-        'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes, 'd2h_bytes_per_step': 32,
-                'ms_per_step': ms_e2e / args.steps},
+        'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
+        'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
+                   'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
+                   'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms,
+                   'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0)},
+        'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes,
+                'd2h_bytes_per_step': 32 if not render_mode else scene.out_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': roof,
-        'step_ms': [round(x, 1) for x in per_step], 'step_ms_e2e': [round(x, 1) for x in per_step_e2e],
+        'step_ms': [round(x, 2) for x in per_step], 'step_ms_e2e': [round(x, 2) for x in per_step_e2e],
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
-        'map_maintenance': maint,
     }
+    if render_mode:
+        out['knn'] = scene.knn_stats()
+        knn_ms = prof['knn'][0]
+        out['value_knn_excluded'] = n_prof / max((tot_kernel_ms - knn_ms) * 1e-3, 1e-9)
+        out['roofline']['hbm_whole_forward'] = {'achieved': n_prof * bytes_fwd / (tot_kernel_ms * 1e-3) / 1e9, 'peak': hbm_peak,
+                                                 'frac': n_prof * bytes_fwd / (tot_kernel_ms * 1e-3) / 1e9 / hbm_peak, 'unit': 'GB/s'}
     if world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline_sample(args.points)
+        out['cpu_baseline'] = cpu_baseline_sample(args.config, points)
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + '\n').encode())
     if dist is not None:
@@ -362,28 +513,30 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# reference arm: the reference algorithm (CPU oracle port) on the host cores, same iteration shells
+# reference arm: the reference algorithm (CPU oracle port) on the host cores, same iteration shells, same iteration mix
 # ---------------------------------------------------------------------------------------------------------------------
 class CpuScene:
-    def __init__(self, n_points, n_frames):
+    def __init__(self, wl, n_points, n_frames):
         from scipy.spatial import cKDTree
         from point_slam_b200.src.conv_onet import config as model_config
-        self.cfg = make_cfg('replica', 'cpu')
+        self.wl, self.S = wl, wl['S']
+        self.cfg = make_cfg(wl['dataset'], 'cpu', **{'rendering.N_surface': wl['S']})
         torch.manual_seed(1219)
         self.decoders = model_config.get_model(self.cfg)
         sd = load_decoder_state()
         emb = sd.pop('color_decoder.embedder._B')
         self.decoders.load_state_dict(sd, strict=True)
         self.decoders.color_decoder.embedder._B = emb
+        self.rel = bool(self.cfg['model']['encode_rel_pos_in_col'])
         cloud = synth.make_cloud(n_points, seed=1219)
         gf, cf = synth.make_features(n_points, seed=1219)
         self.cloud = torch.from_numpy(cloud)
         self.geo, self.col = torch.from_numpy(gf), torch.from_numpy(cf)
         self.tree = cKDTree(cloud.astype(np.float64))
         self.frames = []
-        for f in make_frames(n_frames + 1, seed=1219):
+        for f in make_frames(n_frames + 1, seed=1219, noise=wl.get('noise', False), holes=wl.get('holes', 0.0)):
             self.frames.append(dict(color=torch.from_numpy(f['color']), depth=torch.from_numpy(f['depth']),
-                                    dyn_r_query=torch.from_numpy(f['dyn_r_query']),
+                                    dyn_r_query=torch.from_numpy(f['dyn_r_query']), dyn_r_add=torch.from_numpy(f['dyn_r_add']),
                                     c2w=torch.from_numpy(f['c2w'][:3, :4].astype(np.float32)), c2w64=f['c2w']))
         self.rng = np.random.default_rng(7)
 
@@ -401,61 +554,135 @@ class CpuScene:
         P['color_decoder.embedder._B'] = decoders.color_decoder.embedder._B
         rg = torch.zeros([32]).normal_(mean=0, std=0.01)
         rc = torch.zeros([32]).normal_(mean=0, std=0.01)
-        return O.render_batch_ray(P, rays_d, rays_o, gt_depth, stage, self.cloud, npc_geo_feats, npc_col_feats, S=S,
+        return O.render_batch_ray(P, rays_d, rays_o, gt_depth, stage, self.cloud, npc_geo_feats, npc_col_feats, S=self.S,
                                   is_tracker=is_tracker, radius_query=0.08, dynamic_r_query=dynamic_r_query, rand_geo=rg,
-                                  rand_col=rc, coef=0.1, encode_rel_pos=True, tree=self.tree)
+                                  rand_col=rc, coef=0.1, encode_rel_pos=self.rel, tree=self.tree)
+
+    def map_update(self, cur):
+        """add_neural_points on 6000 + 1000 pixels (kept-location test only: the appended points are not indexed, like a frame
+        that adds nothing) and the frustum feature selection -- the CPU restatements of oracle/point_slam_oracle.py."""
+        from oracle import point_slam_oracle as O
+        from point_slam_b200.src import common
+        for n_pix, grad in ((6000, False), (1000, True)):
+            pix = torch.from_numpy(self.rng.integers(0, INTR['H'] * INTR['W'], n_pix))
+            j, i = pix // INTR['W'], pix % INTR['W']
+            ro, rd = common.get_rays_from_uv(i.float(), j.float(), cur['c2w'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], 'cpu')
+            gd = cur['depth'][j, i]
+            keep = gd > 0
+            O.add_points(self.cloud, ro[keep], rd[keep], gd[keep], dynamic_radius=cur['dyn_r_add'][j, i][keep], is_pts_grad=grad,
+                         tree=self.tree)
+        return torch.from_numpy(O.frustum_indices(self.cloud.numpy(), cur['c2w64'].astype(np.float32), cur['depth'].numpy(), INTR['H'],
+                                                  INTR['W'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], edge=-4))
 
     def step(self, k, track_iters, map_iters, map_pix):
+        """Frame k with `track_iters` tracking and `map_iters` mapping iterations (first geo_iters(map_iters) geometry-stage)."""
+        wl = self.wl
         cur = self.frames[1 + k]
         samples = 0
+        tc = self.cfg['tracking']
         cam = cam_tensor_from_c2w(cur['c2w64'], 0.01, self.rng).requires_grad_(True)
-        opt = torch.optim.Adam([cam], lr=0.002)
+        opt = torch.optim.Adam([cam], lr=tc['lr'])
         for _ in range(track_iters):
             _, n = IT.tracker_iteration(self.render, self, self.decoders, cam, opt, cur['color'], cur['depth'],
-                                        cur['dyn_r_query'], INTR, TRACK_PIX, 'cpu', self.geo, self.col, self.cloud,
-                                        edge=(100, 100))
-            samples += n * S
-        from oracle import point_slam_oracle as O
-        idx = torch.from_numpy(O.frustum_indices(self.cloud.numpy(), cur['c2w64'].astype(np.float32), cur['depth'].numpy(), INTR['H'],
-                                                 INTR['W'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'], edge=-4))
-        state = IT.MapperState(self, self.decoders, idx)
-        for it in range(map_iters):
-            _, n = IT.mapper_iteration(self.render, self, self.decoders, state, [cur, self.frames[0]], INTR, map_pix, 'cpu',
-                                       'color', self.cloud)
-            samples += n * S
+                                        cur['dyn_r_query'], INTR, wl['track'][1], 'cpu', self.geo, self.col, self.cloud,
+                                        edge=(wl['edge'], wl['edge']))
+            samples += n * self.S
+        if map_iters:
+            idx = self.map_update(cur)
+            state = IT.MapperState(self, self.decoders, idx)
+            g = geo_iters(map_iters)
+            for it in range(map_iters):
+                _, n = IT.mapper_iteration(self.render, self, self.decoders, state, [cur, self.frames[0]], INTR, map_pix, 'cpu',
+                                           'geometry' if it < g else 'color', self.cloud)
+                samples += n * self.S
         return samples
 
 
-CPU_TRACK_ITERS, CPU_MAP_ITERS = 40, 16           # bounded sample of the frame step for the CPU legs (~10 s on the host cores)
+class CpuRenderScene:
+    def __init__(self, wl, n_points, n_frames):
+        self.inner = CpuScene(dict(wl, track=None, map=None, edge=0), n_points, n_frames)
+        self.wl = wl
+        rng = np.random.default_rng(3)
+        self.batches = []
+        for f in self.inner.frames:
+            pix = rng.integers(0, INTR['H'] * INTR['W'], wl['rays'])
+            j, i = pix // INTR['W'], pix % INTR['W']
+            o, dd = synth.pixel_rays(f['c2w64'], INTR['H'], INTR['W'], INTR['fx'], INTR['fy'], INTR['cx'], INTR['cy'])
+            self.batches.append(dict(rays_o=torch.from_numpy(np.broadcast_to(o, (wl['rays'], 3)).astype(np.float32).copy()),
+                                     rays_d=torch.from_numpy(dd[j, i].astype(np.float32)), depth=f['depth'][j, i],
+                                     r_query=f['dyn_r_query'][j, i]))
+
+    def step(self, k, n_rays):
+        b = self.batches[k % len(self.batches)]
+        with torch.no_grad():
+            self.inner.render(None, self.inner.decoders, b['rays_d'][:n_rays], b['rays_o'][:n_rays], 'cpu', 'color',
+                              gt_depth=b['depth'][:n_rays], npc_geo_feats=self.inner.geo, npc_col_feats=self.inner.col,
+                              dynamic_r_query=b['r_query'][:n_rays])
+        return n_rays * self.wl['S']
 
 
-def pick_threads(sc):
+def cpu_sample_sizes(name):
+    """Bounded CPU sample of one step with the SAME iteration mix as the CUDA arm (track : map iterations and the geometry
+    share of the mapping iterations), sized for ~10-20 s on the host cores."""
+    wl = CONFIGS[name]
+    if wl['mode'] == 'render':
+        return None
+    if wl['map']:
+        f = 5                                               # c2: 40 : 60 (25 geometry) -> 8 : 12 (5 geometry)
+        return max(wl['track'][0] // f, 1), max(wl['map'][0] // f, 1)
+    return max(wl['track'][0] // 10, 1), 0                  # c4: 200 -> 20 tracking iterations
+
+
+def pick_threads(step_fn):
     """The faster of {all host threads, 32} torch threads on a small untimed step each (tiny ATen ops oversubscribe a
-    128-thread box: 32 threads were 7x faster there).  Uses frames 0 and 1 of `sc`; independent of --warmup."""
+    128-thread box: 32 threads were 7x faster there)."""
     times = {}
     for k, th in enumerate([os.cpu_count()] + ([32] if os.cpu_count() > 32 else [])):
         torch.set_num_threads(th)
-        sc.step(k, 1, 1, 500)                              # first touch (allocator, thread pool)
+        step_fn(k)                                          # first touch (allocator, thread pool)
         t0 = time.perf_counter()
-        sc.step(k, 2, 1, 500)
+        step_fn(k)
         times[th] = time.perf_counter() - t0
     threads = min(times, key=times.get)
     torch.set_num_threads(threads)
     return threads
 
 
-def cpu_baseline_sample(n_points):
-    """Bounded sample of the same workload on the host cores: 40 tracking iterations (1500 rays) + 16 mapping iterations
-    (5000 rays, colour stage), after untimed warm-ups that also pick the faster of {all, 32} torch threads."""
-    sc = CpuScene(n_points, 3)
-    threads = pick_threads(sc)
+def cpu_run(name, n_points, steps, warmup):
+    """-> (samples/s, threads, seconds, description of the per-step sample)"""
+    wl = CONFIGS[name]
+    if wl['mode'] == 'render':
+        sc = CpuRenderScene(wl, n_points, steps + warmup + 2)
+        n_rays = min(wl['rays'], 1000)
+        threads = pick_threads(lambda k: sc.step(k, 200))
+        for k in range(warmup):
+            sc.step(k, 200)
+        t0 = time.perf_counter()
+        n = sum(sc.step(2 + warmup + k, n_rays) for k in range(steps))
+        dt = time.perf_counter() - t0
+        return n / dt, threads, dt, f'{n_rays} of the {wl["rays"]} rays x {wl["S"]} samples, forward render'
+    r_track, r_map = cpu_sample_sizes(name)
+    sc = CpuScene(wl, n_points, steps + warmup + 2)
+    m_pix = wl['map'][1] if wl['map'] else 0
+    threads = pick_threads(lambda k: sc.step(k, 1, 1 if r_map else 0, 500))
+    for k in range(warmup):
+        sc.step(2 + k, 1, 1 if r_map else 0, 500)
     t0 = time.perf_counter()
-    n = sc.step(2, CPU_TRACK_ITERS, CPU_MAP_ITERS, MAP_PIX)
+    n = sum(sc.step(2 + warmup + k, r_track, r_map, m_pix) for k in range(steps))
     dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-            'sample': f'{CPU_TRACK_ITERS} tracking iterations x {TRACK_PIX} rays + {CPU_MAP_ITERS} mapping iterations x {MAP_PIX} rays (colour stage), '
-                      f'fwd+loss+bwd+Adam, {n_points}-point cloud, S=5, torch {torch.__version__} CPU ({threads} of {os.cpu_count()} threads) + scipy '
-                      f'cKDTree exact kNN; {dt:.1f} s', 'seconds': dt}
+    desc = f'{r_track} of the {wl["track"][0]} tracking iterations x {wl["track"][1]} rays'
+    if r_map:
+        desc += (f' + map update + {r_map} of the {wl["map"][0]} mapping iterations x {m_pix} rays ({geo_iters(r_map)} geometry-stage): '
+                 'same track : map : geometry-stage proportions as the full step')
+    return n / dt, threads, dt, desc
+
+
+def cpu_baseline_sample(name, n_points):
+    v, threads, dt, desc = cpu_run(name, n_points, 1, 0)
+    return {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{desc}; fwd+loss+bwd+Adam through the oracle port of the reference (oracle/point_slam_oracle.py, iteration '
+                      f'shells of point_slam_b200/iteration.py), {n_points}-point cloud, torch {torch.__version__} CPU ({threads} of '
+                      f'{os.cpu_count()} threads) + scipy cKDTree exact kNN; {dt:.1f} s', 'seconds': dt}
 
 
 def run_reference(args):
@@ -463,26 +690,16 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     if rank != 0:
         return
-    sc = CpuScene(args.points, args.steps + args.warmup + 2)
-    threads = pick_threads(sc)
-    for k in range(args.warmup):
-        sc.step(2 + k, 1, 1, 500)
-    t0 = time.perf_counter()
-    samples = 0
-    r_track, r_map = max(CPU_TRACK_ITERS // 2, 1), max(CPU_MAP_ITERS // 2, 1)
-    for k in range(args.steps):
-        samples += sc.step(2 + args.warmup + k, r_track, r_map, MAP_PIX)
-    dt = time.perf_counter() - t0
-    v = samples / dt
-    sample = (f'per step: {r_track} tracking iterations x {TRACK_PIX} rays + {r_map} mapping iterations x {MAP_PIX} rays (colour stage), '
-              f'fwd+loss+bwd+Adam on the host cores ({threads} torch threads of {os.cpu_count()}; oracle port of the reference, exact cKDTree kNN)')
-    out = {'impl': 'reference', 'metric': 'ray-samples/sec (render+kNN+MLP fwd+bwd, Replica-config frame)', 'value': v,
-           'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+    wl = CONFIGS[args.config]
+    points = args.points or wl['points']
+    v, threads, dt, desc = cpu_run(args.config, points, args.steps, args.warmup)
+    sample = f'per step: {desc}; host cores ({threads} torch threads of {os.cpu_count()}; oracle port of the reference, exact cKDTree kNN)'
+    render_mode = wl['mode'] == 'render'
+    out = {'impl': 'reference', 'metric': 'ray-samples/sec (render+kNN+MLP' + (' forward' if render_mode else ' fwd+bwd, frame step') + ')',
+           'value': v, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dt * 1e3 / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-           'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': 'C2 Replica-office0-like frame (same scene/frames as the CUDA arm); each step is a bounded '
-                                  f'sample: {r_track} tracking iterations x {TRACK_PIX} rays + {r_map} mapping iterations x {MAP_PIX} rays',
-                      'points': args.points},
+           'dtype': 'f32', 'data': 'synthetic', 'config': dict(workload_config(args.config, points), parallelism=f'scene-per-gpu x{world}'),
+           'sample': sample,
            'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
            'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
@@ -494,7 +711,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--points', type=int, default=500000)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--points', type=int, default=0, help='override the cloud size of the configuration')
+    ap.add_argument('--share-map', action='store_true', help='N > 1: one scene replicated on every GPU, rank 0 maps and broadcasts the map delta (NCCL) every step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -68,7 +68,19 @@ typedef struct psl_grid {
     float cell;                   /* cell edge length in metres                                       */
     float r_small;                /* first-pass search radius (0 = off): exact early exit when 8 points lie
                                      inside it, else the query radius is searched (see k_knn)            */
+    const struct psl_grid_meta* meta; /* optional DEVICE copy of (capacity, n, r_small): when non-NULL the kernels read these
+                                     three from device memory at run time instead of the launch arguments, so that
+                                     a CUDA graph captured over fixed-capacity buffers stays valid after the cloud
+                                     has grown and the hash has been rebuilt in place (add_neural_points,
+                                     src/neural_point.py:147-164); the host fields must still describe a built grid */
 } psl_grid;
+
+typedef struct psl_grid_meta {    /* 16 bytes in device memory, written by the caller after each (re)build */
+    uint32_t capacity;            /* power of two <= allocated table entries */
+    int32_t n;
+    float r_small;
+    uint32_t reserved;
+} psl_grid_meta;
 
 size_t psl_grid_sort_ws_bytes(int64_t n);
 /* step 1: keys, radix sort, gather.  Writes sorted_pts (n,4), sorted_keys (n) and returns the number
@@ -98,6 +110,13 @@ int psl_raymarch_knn(const psl_grid* grid_host, const float* rays_o, const float
                      int64_t n_rays, int32_t n_samples, const float* t_vals, float near_surface, float far_surface,
                      const float* z_override, const double* r2_ray, double r2_scalar,
                      float* z_vals, float* pos, int32_t* I, float* D, int32_t* nnum, psl_stream_t stream);
+/* the same search with work counters for the bench's roofline line (SURVEY.md section 8d asks for the mean number of candidates
+ * visited per query): stats (4 device uint64, zeroed by the caller) += [candidate points staged, warp search passes, queries,
+ * hash cells probed] */
+int psl_raymarch_knn_stats(const psl_grid* grid_host, const float* rays_o, const float* rays_d, const float* gt_depth,
+                           int64_t n_rays, int32_t n_samples, const float* t_vals, float near_surface, float far_surface,
+                           const float* z_override, const double* r2_ray, double r2_scalar,
+                           float* z_vals, float* pos, int32_t* I, float* D, int32_t* nnum, uint64_t* stats, psl_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * K2+K3  IDW interpolation + per-neighbour colour MLP + geometry/colour MLP decode
@@ -298,6 +317,13 @@ int psl_pose_bwd(const int64_t* pix, int32_t n, int32_t H0, int32_t W0, int32_t 
 int psl_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int64_t* rows, int64_t n_slots,
                   int32_t width, int32_t* step, float lr, float beta1, float beta2, float eps, int32_t zero_grad,
                   psl_stream_t stream);
+/* Tracker pose step (Tracker.py:289-349): torch.optim.Adam on cam = [quat(4), T(3)] with lr_quat / lr_trans (tracking.separate_LR:
+ * lr/5 and lr; one shared step count) and, when best_loss != NULL, the candidate bookkeeping of the tracking loop: if *loss <
+ * *best_loss the pose is copied to best_cam -- the pose this iteration rendered with (candidate_pre_step != 0, the separate_LR
+ * branch) or the stepped pose (candidate_pre_step == 0) -- and *best_loss updated.  One launch. */
+int psl_pose_adam(float* cam, const float* d_cam, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr_quat, float lr_trans,
+                  float beta1, float beta2, float eps, const float* loss, float* best_loss, float* best_cam,
+                  int32_t candidate_pre_step, psl_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * map maintenance between renders

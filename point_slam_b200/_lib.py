@@ -26,7 +26,7 @@ _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, 
 
 class Grid(C.Structure):                                   # psl_grid
     _fields_ = [('sorted_pts', _vp), ('table_keys', _vp), ('table_vals', _vp), ('capacity', C.c_uint32),
-                ('n', _i32), ('cell', _f32), ('r_small', _f32)]
+                ('n', _i32), ('cell', _f32), ('r_small', _f32), ('meta', _vp)]
 
 
 N_PARAMS = 1 + 5 * 4 + 2 + 6 + 5 * 4 + 2                   # 51 pointers in psl_decoder_params
@@ -61,6 +61,8 @@ _SIGS = {
     'psl_knn_query': (C.c_int, [C.POINTER(Grid), _vp, _i64, _vp, _f64, _i32, _vp, _vp, _vp, _vp]),
     'psl_raymarch_knn': (C.c_int, [C.POINTER(Grid), _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _vp, _vp, _f64,
                                    _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psl_raymarch_knn_stats': (C.c_int, [C.POINTER(Grid), _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _vp, _vp, _f64,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_packed_params_floats': (_sz, []),
     'psl_decode_save_floats_per_sample': (_sz, [C.POINTER(DecodeCfg)]),
     'psl_decode_bwd_ws_bytes': (_sz, [_i64]),
@@ -79,6 +81,7 @@ _SIGS = {
     'psl_shell_loss': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     'psl_pose_bwd': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_adam_rows': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _f32, _f32, _i32, _vp]),
+    'psl_pose_adam': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
     'psl_composite_fwd': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_composite_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_rays_bwd': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

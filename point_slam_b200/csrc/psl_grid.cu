@@ -114,10 +114,12 @@ struct KnnArgs {
     int seg;                // queries per segment (S for rays)
     const double* r2; double r2_scalar; int r2_group;
     int* I; float* D; int* nnum;
+    unsigned long long* stats;   // optional counters: [0] candidates staged, [1] warp passes, [2] queries, [3] cells probed
 };
 
 template <bool RAYS>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, long long n_work, int n_chunks) {
+    grid_resolve(g);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_cand_all = reinterpret_cast<float4*>(smem_raw);
     unsigned long long* s_best_all =
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
         int nstaged = 0;
         auto flush = [&]() {
             __syncwarp();
+            if (a.stats && lane == 0) atomicAdd(a.stats, (unsigned long long)nstaged);
             for (int s = 0; s < cnt; ++s) {
                 const float sx = __shfl_sync(0xffffffffu, qx, s), sy = __shfl_sync(0xffffffffu, qy, s),
                             sz = __shfl_sync(0xffffffffu, qz, s);
@@ -243,6 +246,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(GridDev g, KnnArgs a, lo
             const int nx = cx1 - cx0 + 1, ny = cy1 - cy0 + 1, nz = cz1 - cz0 + 1;
             long long ncell = (long long)nx * ny * nz;
             if (nx <= 0 || ny <= 0 || nz <= 0 || ncell > (1ll << 22)) ncell = 0;   // NaN / absurd radius: no neighbours
+            if (a.stats && lane == 0) {
+                atomicAdd(a.stats + 1, 1ull);
+                atomicAdd(a.stats + 3, (unsigned long long)ncell);
+                if (pass == (small_pass ? 0 : 1)) atomicAdd(a.stats + 2, (unsigned long long)cnt);
+            }
             for (long long base = 0; base < ncell; base += 32) {
                 const long long ci = base + lane;
                 uint2 rng = make_uint2(0u, 0u);
@@ -426,5 +434,21 @@ extern "C" int psl_raymarch_knn(const psl_grid* grid_host, const float* rays_o, 
     a.near_s = near_surface; a.far_s = far_surface; a.z_vals = z_vals; a.pos_out = pos;
     a.m = n_rays * n_samples; a.seg = n_samples; a.r2 = r2_ray; a.r2_scalar = r2_scalar; a.r2_group = n_samples;
     a.I = I; a.D = D; a.nnum = nnum;
+    return launch_knn<true>(g, a, as_stream(stream));
+}
+
+extern "C" int psl_raymarch_knn_stats(const psl_grid* grid_host, const float* rays_o, const float* rays_d,
+                                      const float* gt_depth, int64_t n_rays, int32_t n_samples, const float* t_vals,
+                                      float near_surface, float far_surface, const float* z_override, const double* r2_ray,
+                                      double r2_scalar, float* z_vals, float* pos, int32_t* I, float* D, int32_t* nnum,
+                                      uint64_t* stats, psl_stream_t stream) {
+    GridDev g;
+    if (int e = make_grid_dev(grid_host, &g)) return e;
+    PSL_REQUIRE(n_rays >= 0 && n_samples >= 1 && stats, "bad ray/sample count or NULL stats");
+    KnnArgs a{};
+    a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth; a.t_vals = t_vals; a.z_override = z_override;
+    a.near_s = near_surface; a.far_s = far_surface; a.z_vals = z_vals; a.pos_out = pos;
+    a.m = n_rays * n_samples; a.seg = n_samples; a.r2 = r2_ray; a.r2_scalar = r2_scalar; a.r2_group = n_samples;
+    a.I = I; a.D = D; a.nnum = nnum; a.stats = reinterpret_cast<unsigned long long*>(stats);
     return launch_knn<true>(g, a, as_stream(stream));
 }

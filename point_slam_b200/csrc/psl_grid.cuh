@@ -13,7 +13,18 @@ struct GridDev {
     int n;
     float inv_cell;
     float r_small;      // radius of the first search pass (0 = single pass with the full query radius)
+    const psl_grid_meta* meta;   // device-side (capacity, n, r_small) overriding the launch-time values (graph replays)
 };
+
+// kernels call this first: with a device meta block the launch-time copies are stale after an in-place rebuild
+__device__ __forceinline__ void grid_resolve(GridDev& g) {
+    if (g.meta) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(g.meta));
+        g.mask = m.x ? m.x - 1u : 0u;
+        g.n = (int)m.y;
+        g.r_small = __uint_as_float(m.z);
+    }
+}
 
 __device__ __forceinline__ uint2 grid_lookup(const GridDev& g, uint64_t key) {
     uint32_t slot = (uint32_t)mix64(key) & g.mask;
@@ -37,6 +48,7 @@ static inline int make_grid_dev(const psl_grid* gh, GridDev* g) {
     g->n = gh->n;
     g->inv_cell = 1.0f / gh->cell;
     g->r_small = gh->r_small;
+    g->meta = gh->meta;
     return 0;
 }
 

@@ -40,6 +40,7 @@ __global__ void k_add_valid(const float* __restrict__ depth, int n, int* __restr
 __global__ void __launch_bounds__(256) k_add_probe(GridDev g, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                    const float* __restrict__ depth, int n, const int* __restrict__ valid_rank,
                                                    const double* __restrict__ r2, double r2_scalar, int* __restrict__ keep) {
+    grid_resolve(g);
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {

@@ -320,6 +320,35 @@ __global__ void k_adam_rows(AdamArgs a) {
     }
 }
 
+// ---- pose step of the tracker: Adam on [quat(4), T(3)] with separate learning rates + the reference's candidate bookkeeping --------
+// Tracker.py:289-349: with tracking.separate_LR the quaternion steps with lr/5 (two parameter groups of ONE optimizer, hence one
+// shared step count); the frame's result is the pose of the iteration with the smallest loss -- the pose that iteration RENDERED
+// with when separate_LR is on (camera_tensor is re-built with torch.cat before each call), the stepped pose otherwise
+// (the Variable is updated in place before .detach().clone()).
+__global__ void k_pose_adam(float* cam, const float* d_cam, float* m, float* v, int* step, float lr_q, float lr_t, float b1, float b2,
+                            float eps, const float* loss, float* best_loss, float* best_cam, int cand_pre_step) {
+    const int i = threadIdx.x;
+    const int t_new = step[0] + 1;
+    __syncthreads();
+    if (i == 0) step[0] = t_new;
+    const bool better = best_loss && loss[0] < best_loss[0];
+    float p = 0.f, p_old = 0.f;
+    if (i < 7) {
+        const float t = (float)t_new;
+        const float lr = i < 4 ? lr_q : lr_t;
+        const float step_size = lr / (1.0f - powf(b1, t)), isb = 1.0f / sqrtf(1.0f - powf(b2, t));
+        float mm = m[i], vv = v[i];
+        p_old = cam[i];
+        p = adam_update(p_old, d_cam[i], mm, vv, b1, b2, step_size, isb, eps);
+        m[i] = mm; v[i] = vv; cam[i] = p;
+    }
+    __syncthreads();
+    if (better) {
+        if (i < 7) best_cam[i] = cand_pre_step ? p_old : p;
+        if (i == 0) best_loss[0] = loss[0];
+    }
+}
+
 }  // namespace psl
 
 using namespace psl;
@@ -399,6 +428,18 @@ extern "C" int psl_adam_rows(float* param, float* grad, float* exp_avg, float* e
     const unsigned nb = vec ? nblk(n_slots * (width / 4), 256) : nblk(n_slots * width, 256);
     if (vec) k_adam_rows<4><<<nb < cap ? nb : cap, 256, 0, st>>>(a);
     else k_adam_rows<1><<<nb < cap ? nb : cap, 256, 0, st>>>(a);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int psl_pose_adam(float* cam, const float* d_cam, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr_quat, float lr_trans,
+                             float beta1, float beta2, float eps, const float* loss, float* best_loss, float* best_cam,
+                             int32_t candidate_pre_step, psl_stream_t stream) {
+    PSL_REQUIRE(cam && d_cam && exp_avg && exp_avg_sq && step, "NULL argument");
+    PSL_REQUIRE(!best_loss || (loss && best_cam), "candidate bookkeeping needs loss and best_cam");
+    TimingScope ts(T_SHELL, as_stream(stream));
+    k_pose_adam<<<1, 32, 0, as_stream(stream)>>>(cam, d_cam, exp_avg, exp_avg_sq, step, lr_quat, lr_trans, beta1, beta2, eps, loss,
+                                                 best_loss, best_cam, candidate_pre_step);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -9,8 +9,18 @@ _BASE = {
     'use_dynamic_radius': True,
     'model': {'c_dim': 32, 'exposure_dim': 8, 'pos_embedding_method': 'fourier', 'encode_rel_pos_in_col': True,
               'encode_exposure': False, 'use_view_direction': False, 'encode_viewd': True},
-    'mapping': {'device': 'cuda:0'},
-    'tracking': {'device': 'cuda:0'},
+    # caller-side keys the iteration shells read (Tracker.py:46-60, Mapper.py:40-80); defaults of configs/point_slam.yaml:23-83
+    'mapping': {'device': 'cuda:0', 'BA': False, 'geo_iter_ratio': 0.4, 'geo_iter_first': 400, 'every_frame': 5, 'pixels': 1000,
+                'iters': 400, 'iters_first': 1500, 'pixels_adding': 6000, 'pixels_based_on_color_grad': 0, 'w_color_loss': 0.1,
+                'frustum_edge': -4, 'min_iter_ratio': 0.95, 'mapping_window_size': 5, 'fix_geo_decoder': True,
+                'fix_color_decoder': False, 'frustum_feature_selection': True, 'keyframe_every': 50,
+                'init': {'geometry': {'decoders_lr': 0.001, 'geometry_lr': 0.03, 'color_lr': 0.0},
+                         'color': {'decoders_lr': 0.005, 'geometry_lr': 0.005, 'color_lr': 0.005}},
+                'stage': {'geometry': {'decoders_lr': 0.001, 'geometry_lr': 0.03, 'color_lr': 0.0},
+                          'color': {'decoders_lr': 0.005, 'geometry_lr': 0.005, 'color_lr': 0.005}}},
+    'tracking': {'device': 'cuda:0', 'lr': 0.002, 'pixels': 200, 'iters': 20, 'w_color_loss': 0.5, 'separate_LR': True,
+                 'handle_dynamic': True, 'use_color_in_tracking': True, 'depth_limit': False, 'sample_with_color_grad': False,
+                 'ignore_edge_W': 20, 'ignore_edge_H': 20, 'const_speed_assumption': True, 'gt_camera': False},
     'cam': {'H': 480, 'W': 640, 'fx': 517.3, 'fy': 516.5, 'cx': 318.6, 'cy': 255.3, 'crop_edge': 0},
     'rendering': {'N_surface': 5, 'near_end': 0.3, 'near_end_surface': 0.98, 'far_end_surface': 1.02,
                   'sigmoid_coef_tracker': 0.1, 'sigmoid_coef_mapper': 0.1, 'sample_near_pcl': True},
@@ -20,11 +30,20 @@ _BASE = {
                    'far_end_surface': 1.02, 'nlist': 400, 'nprobe': 4, 'fix_interval_when_add_along_ray': False},
 }
 _DATASET = {
-    'replica': {'rendering': {'sample_near_pcl': False}},
-    'tum': {'model': {'encode_rel_pos_in_col': False}},
+    'replica': {'rendering': {'sample_near_pcl': False},
+                'tracking': {'ignore_edge_W': 100, 'ignore_edge_H': 100, 'pixels': 1500, 'iters': 40},
+                'mapping': {'keyframe_every': 20, 'mapping_window_size': 12, 'pixels': 5000, 'pixels_based_on_color_grad': 1000,
+                            'iters': 300}},
+    'tum': {'model': {'encode_rel_pos_in_col': False},
+            'tracking': {'separate_LR': False, 'pixels': 5000, 'iters': 200, 'sample_with_color_grad': True},
+            'mapping': {'every_frame': 2, 'mapping_window_size': 10, 'pixels': 10000, 'iters_first': 500, 'geo_iter_first': 200,
+                        'iters': 150}},
     'scannet': {'model': {'encode_exposure': True, 'encode_rel_pos_in_col': False, 'encode_viewd': False},
                 'rendering': {'near_end_surface': 0.96, 'far_end_surface': 1.04},
-                'pointcloud': {'near_end_surface': 0.96, 'far_end_surface': 1.04}},
+                'pointcloud': {'near_end_surface': 0.96, 'far_end_surface': 1.04},
+                'tracking': {'separate_LR': False, 'lr': 0.0005, 'pixels': 5000, 'iters': 100, 'sample_with_color_grad': True},
+                'mapping': {'geo_iter_ratio': 0.3, 'mapping_window_size': 20, 'keyframe_every': 10, 'pixels': 10000,
+                            'iters_first': 500, 'geo_iter_first': 200, 'iters': 300}},
 }
 
 

@@ -117,6 +117,28 @@ def mapper_iteration_static(renderer, npc, decoders, state, kfs, intr, n_pixels,
 # the feature rows) done by the library's shell kernels (csrc/psl_shell.cu) and the render called without autograd.
 # One tracking iteration is ~17 kernel launches (was ~290), one colour-stage mapping iteration ~40 (was ~145).
 # ---------------------------------------------------------------------------------------------------------------------
+def require_supported(cfg, who, tracker):
+    """The graph shells implement the branch of Tracker.optimize_cam_in_batch / Mapper.optimize_map that the Replica and TUM
+    configurations take.  Anything else must go through the autograd Renderer path (module swap),
+    which covers every branch -- refuse loudly instead of optimising a different loss."""
+    bad = []
+    if cfg['model']['encode_exposure']:
+        bad.append('model.encode_exposure (per-frame exposure affine: Tracker.py:151-157, Mapper.py:531-548)')
+    t, m = cfg.get('tracking', {}), cfg.get('mapping', {})
+    if tracker:
+        if not t.get('use_color_in_tracking', True):
+            bad.append('tracking.use_color_in_tracking = False')
+        if not t.get('handle_dynamic', True):
+            bad.append('tracking.handle_dynamic = False (median gate, Tracker.py:167-169)')
+        if t.get('depth_limit', False):
+            bad.append('tracking.depth_limit')
+    elif m.get('BA', False):
+        bad.append('mapping.BA (pose optimisation inside the mapper, Mapper.py:377-392)')
+    if bad:
+        raise NotImplementedError(f'{who}: configuration not covered by the fused iteration shells: ' + '; '.join(bad) +
+                                  ' -- use the Renderer / autograd path for this configuration')
+
+
 def _render_settings(renderer, npc, decoders, stage, is_tracker):
     return decoders.settings(stage, renderer.N_surface, is_tracker, coef=renderer.sigmoid_coefficient,
                              near_surface=renderer.near_end_surface, far_surface=renderer.far_end_surface,
@@ -138,13 +160,15 @@ def _sample(lib, pix, K, per, H, W, H0, W0, ww, cam, c2w, color, depth, dyn, int
 
 
 def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_depth, dyn_r_query, intr, n_pixels, device,
-                            geo_feats, col_feats, cloud_pos, edge, loss_out, w_color=0.5, pack=None, prepacked=False):
-    """tracker_iteration_static on the shell kernels.  cam (7) plain device tensor; writes d_cam (7) and loss_out ()."""
+                            geo_feats, col_feats, cloud_pos, edge, loss_out, w_color=0.5, pack=None, prepacked=False, pix=None):
+    """tracker_iteration_static on the shell kernels.  cam (7) plain device tensor; writes d_cam (7) and loss_out ().
+    pix: the window-relative flat pixel indices select_uv would draw (common.py:66); None = drawn here from the device RNG."""
     lib = L.load()
     H, W = intr['H'], intr['W']
     H0, W0, ww = edge[0], edge[1], W - 2 * edge[1]
     n = n_pixels
-    pix = torch.randint((H - 2 * H0) * ww, (n,), device=device)
+    if pix is None:
+        pix = torch.randint((H - 2 * H0) * ww, (n,), device=device)
     dyn = dyn_r_query if renderer.use_dynamic_radius else None
     rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, 1, n, H, W, H0, W0, ww, cam, None, gt_color, gt_depth, dyn,
                                                             intr, device)
@@ -183,7 +207,7 @@ class AdamRows:
 
 
 def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, device, stage, cloud_pos, loss_out, w_color=0.1,
-                           apply_adam=True):
+                           apply_adam=True, pix=None):
     """mapper_iteration_static on the shell kernels.  fs: FusedMapper state (full feature tensors updated in place by
     AdamRows through the row list, compact gradients through row_map).  apply_adam=False leaves the gradients in
     fs.adam_geo.grad / fs.adam_col.grad / fs.flat (tests)."""
@@ -193,7 +217,8 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
     per = n_pixels // K
     n = K * per
     color = stage == 'color'
-    pix = torch.randint(H * W, (K, per), device=device)
+    if pix is None:
+        pix = torch.randint(H * W, (K, per), device=device)
     dyn = kfs['dyn_r_query'] if renderer.use_dynamic_radius else None
     rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, K, per, H, W, 0, 0, W, None, kfs['c2w'], kfs['color'],
                                                             kfs['depth'], dyn, intr, device)
@@ -232,6 +257,7 @@ class GraphedTracker:
     """Tracker.optimize_cam_in_batch x n_iters as replays of one captured CUDA graph."""
 
     def __init__(self, renderer, npc, decoders, intr, n_pixels, device, edge=(20, 20), lr=0.002, w_color=0.5):
+        require_supported(npc.cfg, 'GraphedTracker', tracker=True)
         self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.edge, self.w = renderer, npc, decoders, intr, n_pixels, device, edge, w_color
         H, W = intr['H'], intr['W']
         self.color = torch.zeros(H, W, 3, device=device)
@@ -307,6 +333,7 @@ class GraphedMapper:
     def __init__(self, renderer, npc, decoders, intr, n_pixels, device, w_color=0.1, lr_dec=0.005, lr_geo=0.005, lr_col=0.005,
                  u_max=1 << 17):
         self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.w = renderer, npc, decoders, intr, n_pixels, device, w_color
+        require_supported(npc.cfg, 'GraphedMapper', tracker=False)
         self.lrs = (lr_dec, lr_geo, lr_col)
         self.loss = torch.zeros((), device=device)
         self.u_max = int(u_max)
@@ -337,7 +364,7 @@ class GraphedMapper:
         N, U = self.npc.pts_num(), int(indices.shape[0])
         while U > self.u_max:
             self.u_max *= 2
-        key = (N, self.u_max, len(keyframes), self.npc.spatial_hash().sorted_pts.data_ptr())
+        key = (N, self.u_max, len(keyframes), self.npc.storage_gen(), self.npc.spatial_hash().build_gen)
         if key != self.key:
             self._alloc(N, len(keyframes))
             self.key = key
@@ -391,42 +418,60 @@ class GraphedMapper:
 
 
 class FusedTracker:
-    """Tracker.optimize_cam_in_batch x n_iters: every iteration is one replay of a graph of ~17 library kernels
-    (tracker_iteration_fused).  The decoder is frozen while tracking, so its operand images are packed once per frame."""
+    """Tracker.optimize_cam_in_batch x n_iters (Tracker.py:89-186, loop of :332-349): every iteration is one replay of a graph
+    of ~17 library kernels (tracker_iteration_fused + psl_pose_adam).  The decoder is frozen while tracking, so its operand
+    images are packed once per frame.  separate_LR: the quaternion steps with lr/5 (Tracker.py:291-299); `best_cam` is the
+    pose of the iteration with the smallest loss, which is what the reference keeps (candidate_cam_tensor, :340-343).
+    selected (optional, per frame): pre-selected pixel indices for tracking.sample_with_color_grad (Tracker.py:117-129); the
+    per-iteration subset is then drawn on the device (with replacement, where the reference uses np.random.choice without)."""
 
-    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, edge=(20, 20), lr=0.002, w_color=0.5):
+    def __init__(self, renderer, npc, decoders, intr, n_pixels, device, edge=(20, 20), lr=0.002, w_color=0.5, separate_lr=True):
+        require_supported(npc.cfg, 'FusedTracker', tracker=True)
         self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.edge, self.w = renderer, npc, decoders, intr, n_pixels, device, edge, w_color
         H, W = intr['H'], intr['W']
         self.color = torch.zeros(H, W, 3, device=device)
         self.depth = torch.zeros(H, W, device=device)
         self.dyn = torch.zeros(H, W, dtype=torch.float64, device=device)
         self.cam = torch.zeros(7, device=device)
+        self.lr, self.separate_lr = float(lr), bool(separate_lr)
         self.adam = AdamRows(1, 7, device, lr)
         self.loss = torch.zeros((), device=device)
+        self.best_loss = torch.full((1,), 1e20, device=device)
+        self.best_cam = torch.zeros(7, device=device)
         self.pack = ops.PackedDecoder(device)
+        self.pix = None                       # fixed pixel batch (tests); None = device RNG per iteration
         self.graph = None
         self.key = None
+        self.captures = 0
 
     def _iter(self):
         tracker_iteration_fused(self.r, self.npc, self.dec, self.cam, self.adam.grad, self.color, self.depth, self.dyn, self.intr,
                                 self.n, self.dev, self.npc.get_geo_feats(), self.npc.get_col_feats(), self.npc.cloud_pos_tensor(),
-                                self.edge, self.loss, self.w, pack=self.pack, prepacked=True)
-        self.adam.step(self.cam, None, zero_grad=False)
+                                self.edge, self.loss, self.w, pack=self.pack, prepacked=True, pix=self.pix)
+        a = self.adam
+        L.check(L.load().psl_pose_adam(L.ptr(self.cam), L.ptr(a.grad), L.ptr(a.m), L.ptr(a.v), L.ptr(a.t),
+                                       self.lr * (0.2 if self.separate_lr else 1.0), self.lr, a.betas[0], a.betas[1], a.eps,
+                                       L.ptr(self.loss.reshape(1)), L.ptr(self.best_loss), L.ptr(self.best_cam),
+                                       int(self.separate_lr), L.stream()), 'psl_pose_adam')
 
     def load_frame(self, color, depth, dyn, cam_init):
         self.color.copy_(color, non_blocking=True); self.depth.copy_(depth, non_blocking=True); self.dyn.copy_(dyn, non_blocking=True)
         self.cam.copy_(cam_init)
         self.adam.reset()
+        self.best_loss.fill_(1e20)
+        self.best_cam.copy_(self.cam)
         self.pack.pack(self.dec.kernel_params())           # the mapper may have updated the colour decoder since the last frame
 
     def _graph_key(self):
-        return (self.npc.pts_num(), self.npc.spatial_hash().sorted_pts.data_ptr(), self.npc.get_geo_feats().data_ptr(),
+        # device buffers the captured kernels point at; the cloud may GROW without invalidating the graph (capacity buffers,
+        # sizes read from device memory: ops.SpatialHash), only a re-allocation forces a re-capture
+        return (self.npc.storage_gen(), self.npc.cloud_pos_tensor().data_ptr(), self.npc.get_geo_feats().data_ptr(),
                 self.npc.get_col_feats().data_ptr())
 
     def capture(self):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        cam0 = self.cam.clone()
+        keep = [t.clone() for t in (self.cam, self.best_loss, self.best_cam)]
         with torch.cuda.stream(s):
             self._iter()                                   # lazy initialisation (caches, allocator) outside of the capture
         torch.cuda.current_stream().wait_stream(s)
@@ -434,11 +479,14 @@ class FusedTracker:
         with torch.cuda.graph(self.graph):
             self._iter()
         self.key = self._graph_key()
-        self.cam.copy_(cam0)
+        self.captures += 1
+        for t, k in zip((self.cam, self.best_loss, self.best_cam), keep):
+            t.copy_(k)
         self.adam.reset()
 
     def run(self, n_iters):
-        if self.graph is None or self.key != self._graph_key():    # the cloud changed (add_neural_points): re-capture
+        """-> loss of the last iteration (device scalar); the frame's pose estimate is `best_cam` (Tracker.py:340-349)."""
+        if self.graph is None or self.key != self._graph_key():    # a buffer was re-allocated (capacity doubling): re-capture
             self.capture()
         for _ in range(n_iters):
             self.graph.replay()
@@ -448,31 +496,41 @@ class FusedTracker:
 class FusedMapper:
     """The joint loop of Mapper.optimize_map (Mapper.py:408-568) on the shell kernels, one graph replay per iteration.
 
-    Instead of the reference's slice tensors + index_put / gather round trip, the full feature tensors are optimised in place:
-    `rows` (u_max, padded with -1) lists the frustum-selected points, `row_map` is its inverse; the render backward scatters
-    feature gradients straight into compact (u_max,32) buffers and psl_adam_rows applies torch.optim.Adam's update to exactly
-    those rows.  The colour decoder keeps a torch fused Adam whose .grad tensors are views of one flat buffer that the
-    weight-gradient kernels write.  Graphs are captured once and survive new frusta; they are re-captured only when the
-    cloud (spatial hash / size) changes."""
+    Instead of the reference's slice tensors + index_put / gather round trip, the cloud's feature tensors are optimised IN
+    PLACE: `rows` (u_max, padded with -1) lists the frustum-selected points, `row_map` is its inverse; the render backward
+    scatters feature gradients straight into compact (u_max,32) buffers and psl_adam_rows applies torch.optim.Adam's update to
+    exactly those rows of `npc.get_geo_feats()` / `get_col_feats()` (the reference writes its optimised slices back with
+    update_geo_feats(feats, indices) at the end, Mapper.py:605-610 -- the same end state; tracker and mapper never overlap,
+    Tracker.py:264-266).  The colour decoder keeps a torch fused Adam whose .grad tensors are views of one flat buffer that
+    the weight-gradient kernels write.  Graphs are captured once per stage and survive new frusta AND cloud growth: every
+    captured pointer is a capacity buffer (NeuralPointCloud.reserve, ops.SpatialHash), sizes that change are read from device
+    memory; only a re-allocation (capacity doubling) forces a re-capture."""
 
     def __init__(self, renderer, npc, decoders, intr, n_pixels, device, w_color=0.1, lr_dec=0.005, lr_geo=0.005, lr_col=0.005,
-                 u_max=1 << 17):
+                 u_max=1 << 17, stage_lrs=None):
         self.r, self.npc, self.dec, self.intr, self.n, self.dev, self.w = renderer, npc, decoders, intr, n_pixels, device, w_color
         self.lrs = (lr_dec, lr_geo, lr_col)
+        # per-stage learning rates of the ONE Adam the reference builds per mapped frame (Mapper.py:394-402, 425-432):
+        # {'geometry': (decoders_lr, geometry_lr, color_lr), 'color': (...)}; cfg['mapping']['stage'] (point_slam.yaml:76-84)
+        ms = npc.cfg.get('mapping', {}).get('stage') if stage_lrs is None else stage_lrs
+        self.stage_lrs = ({k: (ms[k]['decoders_lr'], ms[k]['geometry_lr'], ms[k]['color_lr']) for k in ('geometry', 'color')}
+                          if isinstance(ms, dict) and isinstance(ms.get('color'), dict) else
+                          (ms or {'geometry': self.lrs, 'color': self.lrs}))
         self.loss = torch.zeros((), device=device)
+        require_supported(npc.cfg, 'FusedMapper', tracker=False)
         self.u_max = int(u_max)
         self.graphs = {}
         self.key = None
         self.warm = False
         self.n_used = 0
+        self.captures = 0
+        self.pix = None
 
-    def _alloc(self, N, n_kf):
+    def _alloc(self, cap_rows, n_kf):
         H, W = self.intr['H'], self.intr['W']
         d = self.dev
-        self.npc_geo = torch.zeros(N, 32, device=d)
-        self.npc_col = torch.zeros(N, 32, device=d)
         self.rows = torch.full((self.u_max,), -1, dtype=torch.int64, device=d)
-        self.row_map = torch.full((N,), -1, dtype=torch.int32, device=d)
+        self.row_map = torch.full((cap_rows,), -1, dtype=torch.int32, device=d)
         self.adam_geo = AdamRows(self.u_max, 32, d, self.lrs[1])
         self.adam_col = AdamRows(self.u_max, 32, d, self.lrs[2])
         plist = self.dec.kernel_params()
@@ -496,10 +554,13 @@ class FusedMapper:
         u_max = self.u_max
         while U > u_max:
             u_max *= 2
-        key = (N, u_max, len(keyframes), self.npc.spatial_hash().sorted_pts.data_ptr())
+        self.npc_geo, self.npc_col = self.npc.get_geo_feats(), self.npc.get_col_feats()
+        cap_rows = self.npc.feature_capacity()
+        key = (self.npc.storage_gen(), cap_rows, u_max, len(keyframes), self.npc_geo.data_ptr(), self.npc_col.data_ptr(),
+               self.npc.cloud_pos_tensor().data_ptr())
         if key != self.key:
             self.u_max = u_max
-            self._alloc(N, len(keyframes))
+            self._alloc(cap_rows, len(keyframes))
             self.key = key
         self.n_used = U
         with torch.no_grad():
@@ -507,8 +568,6 @@ class FusedMapper:
             self.rows[:U] = indices
             self.row_map.fill_(-1)
             self.row_map[indices] = torch.arange(U, dtype=torch.int32, device=self.dev)
-            self.npc_geo.copy_(self.npc.get_geo_feats())
-            self.npc_col.copy_(self.npc.get_col_feats())
             for i, kf in enumerate(keyframes):
                 self.keyframes['color'][i].copy_(kf['color']); self.keyframes['depth'][i].copy_(kf['depth'])
                 self.keyframes['c2w'][i].copy_(kf['c2w'][:3, :4]); self.keyframes['dyn_r_query'][i].copy_(kf['dyn_r_query'])
@@ -525,8 +584,12 @@ class FusedMapper:
         return [nm in want for nm in ops.PARAM_ORDER]
 
     def _iter(self, stage):
+        lr_dec, lr_geo, lr_col = self.stage_lrs[stage]      # launch constants of this stage's graph
+        self.adam_geo.lr, self.adam_col.lr = float(lr_geo), float(lr_col)
+        for g in self.dec_opt.param_groups:
+            g['lr'] = float(lr_dec)
         mapper_iteration_fused(self.r, self.npc, self.dec, self, self.keyframes, self.intr, self.n, self.dev, stage,
-                               self.npc.cloud_pos_tensor(), self.loss, self.w)
+                               self.npc.cloud_pos_tensor(), self.loss, self.w, pix=self.pix)
 
     def run(self, stage, n_iters):
         done = 0
@@ -543,12 +606,12 @@ class FusedMapper:
             with torch.cuda.graph(g):                      # capture records the iteration, it does not execute it
                 self._iter(stage)
             self.graphs[stage] = g
+            self.captures += 1
         for _ in range(n_iters - done):
             self.graphs[stage].replay()
         return self.loss
 
     def write_back(self):
-        """Optimised rows -> the neural point cloud (Mapper.py:605-610)."""
-        idx = self.rows[:self.n_used]
-        self.npc.update_geo_feats(self.npc_geo[idx], idx)
-        self.npc.update_col_feats(self.npc_col[idx], idx)
+        """Mapper.py:605-610 (update_geo_feats / update_col_feats of the optimised rows): nothing to copy, the rows were
+        optimised in place in the cloud's own feature tensors."""
+        return self.rows[:self.n_used]

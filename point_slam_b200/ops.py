@@ -75,16 +75,50 @@ def _f32c(t):
 # spatial hash
 # ------------------------------------------------------------------------------------------------------------------
 class SpatialHash:
-    """GPU-resident hash grid over the neural point cloud (K0).  Rebuilt on every append (about 1 ms for 2 M points);
-    point indices are stable (the grid stores a sorted copy carrying the original index)."""
+    """GPU-resident hash grid over the neural point cloud (K0).  Rebuilt on every append (about 0.2 ms for 500 k points);
+    point indices are stable (the grid stores a sorted copy carrying the original index).
+
+    All device buffers (sorted copy, table, sort scratch) are allocated for a CAPACITY of points and re-used by every
+    rebuild; the three numbers that change with a rebuild (table size in use, point count, first-pass radius) are also kept
+    in a 16-byte device block (`psl_grid_meta`) that the kernels read at run time.  A CUDA graph captured over this hash
+    therefore stays valid while the cloud grows: `alloc_gen` changes only when a rebuild had to re-allocate (capacity
+    doubling), `build_gen` counts every rebuild (the reference re-trains / re-adds its faiss index the same way,
+    neural_point.py:161-164)."""
 
     def __init__(self, cell: float = 0.08, two_pass: bool = True):
         self.cell = float(cell)
         self.two_pass = two_pass
         self.n = 0
-        self.sorted_pts = self.table_keys = self.table_vals = None
-        self.capacity = 0
-        self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0)
+        self.cap_points = 0
+        self.sorted_pts = self.table_keys = self.table_vals = self._keys = self._ws = self.meta = None
+        self._meta_host = None
+        self.capacity = 0                 # table entries in use (power of two)
+        self.table_alloc = 0              # table entries allocated
+        self.n_cells = 0
+        self.r_small = 0.0
+        self.alloc_gen = 0
+        self.build_gen = 0
+        self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0, None)
+
+    def reserve(self, n_points: int, device):
+        """Buffers for up to `n_points` points (doubling growth).  Returns True when something was re-allocated."""
+        if n_points <= self.cap_points and self.sorted_pts is not None:
+            return False
+        lib = L.load()
+        cap = max(int(n_points), 2 * self.cap_points, 1024)
+        self.cap_points = cap
+        self.sorted_pts = torch.empty((cap, 4), dtype=torch.float32, device=device)
+        self._keys = torch.empty(cap, dtype=torch.int64, device=device)
+        self._ws_bytes = lib.psl_grid_sort_ws_bytes(cap)
+        self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
+        self.table_alloc = 1 << max(4, int(math.ceil(math.log2(2 * cap))))      # worst case: every point in its own cell
+        self.table_keys = torch.empty(self.table_alloc, dtype=torch.int64, device=device)
+        self.table_vals = torch.empty((self.table_alloc, 2), dtype=torch.int32, device=device)
+        if self.meta is None:
+            self.meta = torch.zeros(4, dtype=torch.int32, device=device)
+            self._meta_host = torch.zeros(4, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(4, dtype=torch.int32)
+        self.alloc_gen += 1
+        return True
 
     def build(self, cloud_pos: torch.Tensor):
         lib = L.load()
@@ -92,21 +126,18 @@ class SpatialHash:
         n = pos.shape[0]
         dev = pos.device
         self.n = n
+        self.build_gen += 1
         if n == 0:
-            self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0)
+            self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0, None)
             return self
-        ws_bytes = lib.psl_grid_sort_ws_bytes(n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        self.sorted_pts = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        self.reserve(n, dev)
         n_cells = C.c_int64(0)
-        L.check(lib.psl_grid_sort(L.ptr(pos), n, self.cell, L.ptr(self.sorted_pts), L.ptr(keys), L.ptr(ws), ws_bytes,
-                                  C.byref(n_cells), L.stream()), 'psl_grid_sort')
+        L.check(lib.psl_grid_sort(L.ptr(pos), n, self.cell, L.ptr(self.sorted_pts), L.ptr(self._keys), L.ptr(self._ws),
+                                  self._ws_bytes, C.byref(n_cells), L.stream()), 'psl_grid_sort')
         cap = 1 << max(4, int(math.ceil(math.log2(max(2 * n_cells.value, 2)))))
+        assert cap <= self.table_alloc
         self.capacity = cap
-        self.table_keys = torch.empty(cap, dtype=torch.int64, device=dev)
-        self.table_vals = torch.empty((cap, 2), dtype=torch.int32, device=dev)
-        L.check(lib.psl_grid_hash(L.ptr(keys), n, L.ptr(self.table_keys), L.ptr(self.table_vals), cap, L.stream()),
+        L.check(lib.psl_grid_hash(L.ptr(self._keys), n, L.ptr(self.table_keys), L.ptr(self.table_vals), cap, L.stream()),
                 'psl_grid_hash')
         self.n_cells = n_cells.value
         # first-pass radius: expect ~32 points inside it, estimated from the mean occupancy of the occupied cells
@@ -115,8 +146,13 @@ class SpatialHash:
         if self.two_pass:
             rs = math.sqrt(32.0 * 1.5 * self.cell ** 2 * max(self.n_cells, 1) / (math.pi * n))
             self.r_small = float(min(max(rs, self.cell / 4), self.cell))
+        # device copy of (capacity, n, r_small): stream-ordered after the rebuild, before the next query
+        self._meta_host[0] = cap if cap < (1 << 31) else cap - (1 << 32)
+        self._meta_host[1] = n
+        self._meta_host[2:3] = torch.tensor([self.r_small], dtype=torch.float32).view(torch.int32)
+        self.meta.copy_(self._meta_host, non_blocking=True)
         self.struct = L.Grid(self.sorted_pts.data_ptr(), self.table_keys.data_ptr(), self.table_vals.data_ptr(),
-                             cap, n, self.cell, self.r_small)
+                             cap, n, self.cell, self.r_small, self.meta.data_ptr())
         return self
 
 
@@ -146,6 +182,27 @@ def knn_query(grid: SpatialHash, pos: torch.Tensor, radius: float = 0.08, dynami
     L.check(lib.psl_knn_query(C.byref(grid.struct), L.ptr(pos), M, L.ptr(r2), r2s, int(group), L.ptr(I), L.ptr(D),
                               L.ptr(nn), L.stream()), 'psl_knn_query')
     return D, I, nn
+
+
+def raymarch_knn_stats(grid: SpatialHash, rays_o, rays_d, gt_depth, S, r2_ray=None, radius=0.08, near=0.98, far=1.02):
+    """Work counters of one ray-march + kNN launch (bench.py): -> dict with the mean number of candidate points staged per query
+    (C-bar of SURVEY.md section 8d), hash cells probed per query and the share of warps that needed the second search pass."""
+    lib = L.load()
+    ro, rd, dep = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
+    R = ro.shape[0]
+    dev = ro.device
+    M = R * S
+    z = torch.empty((R, S), dtype=torch.float32, device=dev); pos = torch.empty((M, 3), dtype=torch.float32, device=dev)
+    I = torch.empty((M, 8), dtype=torch.int32, device=dev); D = torch.empty((M, 8), dtype=torch.float32, device=dev)
+    nn = torch.empty((M,), dtype=torch.int32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    L.check(lib.psl_raymarch_knn_stats(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(dep), R, S, L.ptr(surface_t_vals(S, dev)),
+                                       near, far, None, L.ptr(r2_ray), float(np.float32(radius ** 2)), L.ptr(z), L.ptr(pos), L.ptr(I),
+                                       L.ptr(D), L.ptr(nn), L.ptr(stats), L.stream()), 'psl_raymarch_knn_stats')
+    c, passes, q, cells = (int(x) for x in stats.tolist())
+    warps = (R * ((S + 31) // 32))
+    return {'queries': q, 'candidates_per_query': c / max(q, 1), 'cells_probed_per_query': cells / max(q, 1),
+            'second_pass_share_of_warps': max(passes - warps, 0) / max(warps, 1), 'candidate_bytes_per_query': 16.0 * c / max(q, 1)}
 
 
 _T_VALS = {}

@@ -62,6 +62,7 @@ class NeuralPointCloud(object):
         self._input_pending = []           # device chunks (pos, rgb) not yet converted to the host lists
         self._pts_num = 0
         self._indexed = 0                  # number of positions the hash currently covers
+        self._store_gen = 0                # bumped when a position / feature buffer is re-allocated
         self.geo_feats = None
         self.col_feats = None
         self.keyframe_dict = []
@@ -80,6 +81,7 @@ class NeuralPointCloud(object):
     def _cloud_pos(self, value):          # offline tools assign a list (get_mesh_tsdf_fusion.py:66)
         self._pos = torch.as_tensor(value, dtype=torch.float32, device=self.device).reshape(-1, 3)   # adopted by _reserve
         self._pos_list_cache = None
+        self._indexed = 0                  # the hash covers nothing of the new positions until index.add() is called
 
     def cloud_pos(self, index=None):
         return self._cloud_pos if index is None else self._cloud_pos[index]
@@ -161,14 +163,26 @@ class NeuralPointCloud(object):
 
     # ---- index maintenance -----------------------------------------------------------------------------------------
     def _index_add(self, pts):
-        """Cover `pts` with the hash.  When they are the tail of `_pos` (the add_neural_points flow) nothing is copied;
-        a foreign tensor (offline tools) is appended to `_pos` first."""
+        """Cover `pts` with the hash.  When they are the tail of `_pos` (the add_neural_points flow: same storage) nothing
+        is copied; a foreign tensor (offline tools, get_mesh_tsdf_fusion.py:78-79) is appended to `_pos` first."""
         pts = torch.as_tensor(pts, dtype=torch.float32, device=self.device).reshape(-1, 3)
-        if self._pos.shape[0] != self._indexed + pts.shape[0]:
-            self._pos = torch.cat([self._pos[:self._indexed], pts], 0)
+        tail = self._pos[self._indexed:]
+        is_tail = pts.shape[0] == tail.shape[0] and (pts.shape[0] == 0 or pts.data_ptr() == tail.data_ptr() or
+                                                     torch.equal(pts, tail))       # restore flow: a copy of the assigned list
+        if not is_tail:
+            assert tail.shape[0] == 0, ('index.add(x): x is neither the un-indexed tail of the cloud nor a copy of it '
+                                        f'({tail.shape[0]} positions were assigned through _cloud_pos but never indexed)')
+            k = pts.shape[0]
+            src = pts.clone() if k else pts              # `pts` may alias the buffer that _reserve replaces
+            self._pos = self._pos[:self._indexed]
+            self._reserve(k, features=False)
+            self._pos_buf[self._indexed:self._indexed + k] = src
+            self._pos = self._pos_buf[:self._indexed + k]
             self._pos_list_cache = None
+        grew = self._pos.shape[0] != self._indexed
         self._indexed = self._pos.shape[0]
-        self._grid.build(self._pos)
+        if grew or self._grid.build_gen == 0:            # nothing appended: the hash already covers the cloud
+            self._grid.build(self._pos)
         self.index.is_trained = True
 
     def _search_all(self, q):
@@ -179,16 +193,35 @@ class NeuralPointCloud(object):
         return D, I.long()
 
     # ---- point insertion (neural_point.py:91-167) --------------------------------------------------------------------
-    def _reserve(self, extra):
+    def reserve(self, n_points):
+        """Pre-size the position / feature / hash buffers for `n_points` points, so that no append up to that size
+        re-allocates (CUDA graphs captured over the cloud stay valid; see ops.SpatialHash)."""
+        self._reserve(max(int(n_points) - self._pos.shape[0], 0))
+        self._grid.reserve(int(n_points), self.device)
+
+    def feature_capacity(self):
+        """Rows of the feature storage behind get_geo_feats() / get_col_feats() (>= pts_num())."""
+        if self._geo_buf is not None and self.geo_feats is not None and self.geo_feats.data_ptr() == self._geo_buf.data_ptr():
+            return self._geo_buf.shape[0]
+        return 0 if self.geo_feats is None else self.geo_feats.shape[0]
+
+    def storage_gen(self):
+        """Changes whenever a device buffer the render kernels read (positions, features, hash) was re-allocated."""
+        return (self._store_gen, self._grid.alloc_gen)
+
+    def _reserve(self, extra, features=True):
         """Room for `extra` more points behind the indexed ones in the position / feature buffers (amortised doubling).
         Tensors a caller assigned directly (`npc.geo_feats = ...`, `npc._cloud_pos = ...`) are adopted first."""
-        n = self._indexed
+        n = self._pos.shape[0]             # indexed positions + a tail assigned through `_cloud_pos` that index.add() will cover
         need = n + int(extra)
-        if self._pos.data_ptr() != self._pos_buf.data_ptr() or self._pos_buf.shape[0] < need:
+        if (n and self._pos.data_ptr() != self._pos_buf.data_ptr()) or self._pos_buf.shape[0] < need:
             cap = max(need, 2 * self._pos_buf.shape[0], 1024)
             buf = torch.empty((cap, 3), dtype=torch.float32, device=self.device)
-            buf[:n] = self._pos[:n]
+            buf[:n] = self._pos
             self._pos_buf, self._pos = buf, buf[:n]
+            self._store_gen += 1
+        if not features:
+            return
         for name, bufname in (('geo_feats', '_geo_buf'), ('col_feats', '_col_buf')):
             cur, buf = getattr(self, name), getattr(self, bufname)
             rows = 0 if cur is None else cur.shape[0]
@@ -201,6 +234,7 @@ class NeuralPointCloud(object):
                 setattr(self, bufname, nbuf)
                 if cur is not None:
                     setattr(self, name, nbuf[:rows])
+                self._store_gen += 1
 
     def add_neural_points(self, batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color, train=False,
                           is_pts_grad=False, dynamic_radius=None):
@@ -230,8 +264,9 @@ class NeuralPointCloud(object):
         self.geo_feats = self._geo_buf[:rows + n_new]
         self.col_feats = self._col_buf[:rows + n_new]
         pts = self._pos[n0:]
-        self.index.train(pts)
-        self.index.add(pts)
+        if n_new or not self.index.is_trained:           # nothing kept: the hash already covers the cloud (static camera)
+            self.index.train(pts)
+            self.index.add(pts)
         return torch.tensor(n_keep, device=self.device)
 
     def append_points(self, pts, geo_rows, col_rows):

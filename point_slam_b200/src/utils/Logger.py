@@ -58,4 +58,6 @@ def load_neural_point_cloud(npc, ckpt, device):
     cloud_pos = torch.tensor(ckpt['cloud_pos'], device=device)
     npc.index_train(cloud_pos)
     npc.index.add(cloud_pos)
+    assert npc.geo_feats.shape[0] == npc.col_feats.shape[0] == npc.index_ntotal() == npc._pts_num, \
+        'checkpoint is inconsistent: feature rows / positions / pts_num differ'
     return npc.index_ntotal()

@@ -16,7 +16,7 @@ from point_slam_b200 import iteration as IT  # noqa: E402
 n_track = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n_map = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = 'cuda:0'
-scene = bench.GpuScene(0, dev, 500000, 1)
+scene = bench.GpuScene(0, dev, bench.CONFIGS[os.environ.get('PSL_PROF_CONFIG', 'c2')], 500000, 1)
 fh = scene.frames_host[bench.N_KEYFRAMES]
 src = scene.resident[0]
 tr, mp = scene.tracker, scene.mapper
@@ -51,8 +51,8 @@ torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 run(n_track, n_map)
 if os.environ.get('PSL_PROF_MAP', '1') != '0':      # the per-mapped-frame map updates: frustum selection + add_neural_points
+    scene.map_update(src['c2w'], tr.depth, tr.color)
     select()
-    scene.map_maintenance_ms(0, reps=1)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print('done')

@@ -9,7 +9,7 @@ DEV = 'cuda:0'
 
 def _setup():
     import bench
-    scene = bench.GpuScene(0, DEV, 200000, 1)
+    scene = bench.GpuScene(0, DEV, bench.CONFIGS['c2'], 200000, 1)
     return bench, scene
 
 

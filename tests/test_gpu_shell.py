@@ -206,7 +206,7 @@ def test_adam_rows_matches_torch_adam():
 
 def _scene():
     import bench
-    return bench, bench.GpuScene(0, DEV, 200000, 1)
+    return bench, bench.GpuScene(0, DEV, bench.CONFIGS['c2'], 200000, 1)
 
 
 def test_fused_tracker_iteration_matches_static_shell():
@@ -272,7 +272,7 @@ def test_fused_graphs_run_and_optimise():
     bench, scene = _scene()
     cur = scene.resident[0]
     npc, dec, ren = scene.npc, scene.decoders, scene.renderer
-    ft = G.FusedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    ft = G.FusedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100), separate_lr=False)     # one lr, like the torch-shell Adam below
     cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.02, scene.rng).to(DEV)
     ft.load_frame(cur['color'], cur['depth'], cur['dyn_r_query'], cam0)
     l0 = float(ft.run(1))
@@ -315,9 +315,9 @@ def test_fused_graphs_run_and_optimise():
     sel = torch.zeros_like(moved); sel[idx] = True
     assert bool(moved.any()) and not bool((moved & ~sel).any())          # only frustum rows are optimised
     assert any(not torch.equal(a, p.detach()) for a, p in zip(w0, dec.color_decoder.parameters()))
-    before = npc.get_geo_feats().clone()
-    fm.write_back()
-    assert not torch.equal(before, npc.get_geo_feats())
+    # the rows are optimised in place in the cloud's own tensors: write_back (Mapper.py:605-610) has nothing left to copy
+    assert fm.npc_geo.data_ptr() == npc.get_geo_feats().data_ptr() and torch.equal(fm.write_back(), idx)
+    assert not torch.equal(g0, npc.get_geo_feats())
     n_graphs = len(fm.graphs)
     fm.begin_frame(idx[: idx.shape[0] // 2], [cur] + scene.keyframes)    # a different frustum re-uses the graphs
     le = float(fm.run('color', 3))
@@ -415,3 +415,41 @@ def test_shell_entry_points_reject_bad_arguments():
     assert lib.psl_sample_rays(L.ptr(pix), 1, 4, 480, 640, 0, 0, 640, None, None, L.ptr(d), L.ptr(d), None, 1., 1., 0., 0., L.ptr(o), L.ptr(o),
                                L.ptr(o), L.ptr(o), None, L.stream()) != 0                                                     # neither cam nor c2w
     torch.cuda.synchronize()
+
+
+def test_iteration_graphs_survive_cloud_growth():
+    """add_neural_points between frames (Mapper.py:317,328) must not force a re-capture: the hash is rebuilt in place in its
+    capacity buffers and the kernels read its size from device memory (ops.SpatialHash / psl_grid_meta).  The replayed graph
+    must see the NEW cloud: same result as a tracker captured from scratch on the grown cloud."""
+    from point_slam_b200 import graphed as G
+    from point_slam_b200.src import common
+    bench, scene = _scene()
+    cur = scene.resident[0]
+    npc, dec, ren = scene.npc, scene.decoders, scene.renderer
+    ft = G.FusedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    cam0 = bench.cam_tensor_from_c2w(scene.frames_host[bench.N_KEYFRAMES]['c2w'], 0.02, scene.rng).to(DEV)
+    ft.load_frame(cur['color'], cur['depth'], cur['dyn_r_query'], cam0)
+    ft.run(3)
+    assert ft.captures == 1
+    # carve a hole into the view by adding points in front of the camera: a batch of rays at 60 % of the sensor depth
+    n0 = npc.pts_num()
+    pix = torch.randint(0, bench.INTR['H'] * bench.INTR['W'], (4000,), device=DEV)
+    j, i = pix // bench.INTR['W'], pix % bench.INTR['W']
+    ro, rd = common.get_rays_from_uv(i.float(), j.float(), cur['c2w'], bench.INTR['fx'], bench.INTR['fy'], bench.INTR['cx'], bench.INTR['cy'], DEV)
+    k = npc.add_neural_points(ro, rd, cur['depth'][j, i] * 0.6, cur['color'][j, i])
+    assert int(k) > 1000 and npc.pts_num() == n0 + 3 * int(k)
+    gen = npc.spatial_hash().build_gen
+    ft.load_frame(cur['color'], cur['depth'] * 0.6, cur['dyn_r_query'], cam0)      # the frame now looks at the new points
+    torch.manual_seed(3)
+    ft.run(5)
+    assert ft.captures == 1, 'the tracker graph was re-captured although no buffer was re-allocated'
+    fresh = G.FusedTracker(ren, npc, dec, bench.INTR, 1500, DEV, edge=(100, 100))
+    fresh.load_frame(cur['color'], cur['depth'] * 0.6, cur['dyn_r_query'], cam0)
+    fresh.capture()
+    torch.manual_seed(3)
+    fresh.run(5)
+    assert npc.spatial_hash().build_gen == gen
+    assert torch.equal(ft.cam, fresh.cam) and torch.equal(ft.loss, fresh.loss), (ft.cam, fresh.cam)
+    # a frame that adds nothing leaves the hash alone (no rebuild, ADVICE r1)
+    k2 = npc.add_neural_points(ro, rd, cur['depth'][j, i] * 0.6, cur['color'][j, i])
+    assert int(k2) == 0 and npc.spatial_hash().build_gen == gen

@@ -141,26 +141,25 @@ print('W16-OK')
 
 @pytest.mark.parametrize('mode', [2, 3])
 @pytest.mark.parametrize('K,N', [(16, 16), (48, 128), (64, 128), (128, 32), (128, 128), (208, 128)])
-def test_tc_gemm_f16_bf16_planes(mode, K, N):
-    """kind::f16 MMAs on 16-bit operand planes (hi = f16, lo = bf16(a - hi), A / B formats mixed per instruction):
-    the three products hi*hi + lo*hi + hi*lo must reproduce the fp32 product to ~2^-20."""
+def test_tc_gemm_f16_planes(mode, K, N):
+    """kind::f16 MMAs on 16-bit operand planes (hi = f16(a), lo = f16(a - hi); TS form keeps two k per TMEM column): the three
+    products hi*hi + lo*hi + hi*lo must reproduce the fp32 product as well as 3xTF32 does, at half the TMEM / shared-memory
+    footprint and twice the MMA rate.  (Mixing f16 and bf16 operands in one instruction faults on sm_100a:
+    profiles/r02_s2_f16_planes_probe.log.)"""
     from point_slam_b200 import _lib as L
     lib = L.load()
     if mode == 2 and K > 128:
         pytest.skip('TS-form A planes hold K <= 128')
     g = torch.Generator().manual_seed(K * 1000 + N + mode)
     A = (torch.randn(128, K, generator=g) * 3).cuda()
-    A[:, 0] *= 1e-4                       # small magnitudes: the f16 plane goes subnormal, the bf16 residual must carry them
+    A[:, 0] *= 1e-4                       # small magnitudes: both planes go subnormal (absolute error <= 3e-8)
     W = torch.randn(N, K, generator=g).cuda()
     ref = (A.double() @ W.double().t())
     err32 = float(((A @ W.t()).double() - ref).abs().max() / ref.abs().max())
-    errs = {}
-    for variant in (0, 1):
-        D = torch.zeros(128, N, device='cuda')
-        scratch = torch.empty(N * K, device='cuda')
-        L.check(lib.psl_tc_gemm_test_h(L.ptr(A), L.ptr(W), L.ptr(D), L.ptr(scratch), K, N, mode, variant, L.stream()),
-                'psl_tc_gemm_test_h')
-        torch.cuda.synchronize()
-        errs[variant] = float((D.double() - ref).abs().max() / ref.abs().max())
-    print(f'mode {mode} K {K} N {N}: f16/bf16 planes err {errs[0]:.2e} (halves swapped {errs[1]:.2e}; fp32 matmul err {err32:.2e})')
-    assert errs[0] < 4e-6
+    D = torch.zeros(128, N, device='cuda')
+    scratch = torch.empty(N * K, device='cuda')
+    L.check(lib.psl_tc_gemm_test_h(L.ptr(A), L.ptr(W), L.ptr(D), L.ptr(scratch), K, N, mode, 2, L.stream()), 'psl_tc_gemm_test_h')
+    torch.cuda.synchronize()
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    print(f'mode {mode} K {K} N {N}: f16 hi/lo planes err {err:.2e} (fp32 matmul err {err32:.2e})')
+    assert err < 2e-6

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.DecoderParams) == 8 * _lib.N_PARAMS
     assert ctypes.sizeof(_lib.DecodeCfg) == 40
-    assert ctypes.sizeof(_lib.Grid) == 40       # 3 pointers + u32 + i32 + 2 floats
+    assert ctypes.sizeof(_lib.Grid) == 48       # 3 pointers + u32 + i32 + 2 floats + the device meta pointer
     cfg = _lib.DecodeCfg(1, 1, 0, 0, 2, 5, 0, 0, 0.0064)
     assert _lib.load().psl_decode_save_floats_per_sample(ctypes.byref(cfg)) == 2304
     cfg.encode_rel_pos = 0

@@ -77,6 +77,27 @@ def _worker(rank, world, port, ret):
         dist.all_gather(sigs, sig)
         assert all(torch.equal(s, sigs[0]) for s in sigs), 'replicas differ after the delta broadcast'
         assert npc.pts_num() == 1030
+        # the same exchange as ONE collective (fixed-capacity DeltaChannel): a second delta on top of the first
+        ch = PL.DeltaChannel('cpu', nd, k_max=64, u_max=16)
+        delta = None
+        if rank == 0:
+            n0 = npc.pts_num()
+            g = torch.Generator().manual_seed(12)
+            npc.append_points(torch.randn(7, 3, generator=g), torch.randn(7, 32, generator=g), torch.randn(7, 32, generator=g))
+            idx = torch.tensor([0, 1031, 12])
+            npc.update_geo_feats(torch.randn(3, 32, generator=g), idx)
+            with torch.no_grad():
+                for p in dec.color_decoder.parameters():
+                    p.mul_(1.01)
+            delta = PL.make_delta(npc, dec, n0, idx)
+        PL.apply_delta(npc, dec, ch.broadcast(delta, 0))
+        flat = torch.cat([npc.cloud_pos_tensor().reshape(-1), npc.get_geo_feats().reshape(-1), npc.get_col_feats().reshape(-1),
+                          torch.cat([p.detach().reshape(-1) for p in dec.color_decoder.parameters()])]).double()
+        sig = torch.stack([flat.sum(), (flat * torch.arange(flat.numel(), dtype=torch.float64)).sum(), torch.tensor(float(npc.pts_num()))])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        assert all(torch.equal(s, sigs[0]) for s in sigs), 'replicas differ after the single-collective delta'
+        assert npc.pts_num() == 1037
         # row-sharded image: each rank renders its rows of a synthetic "image"
         H, W = 11, 7
         def render_rows(r0, r1):
