@@ -179,11 +179,9 @@ def draw_rand_vecs(seed):
     return a, b
 
 
-def load_mapper_class():
-    """The reference `Mapper` class (src/Mapper.py), imported for its stateless helpers (get_mask_from_c2w)."""
-    assert os.path.isdir(REF_ROOT), 'reference tree not present (this harness only runs in the build container)'
-    _install_stubs()
-
+def _stub_caller_imports():
+    """Import-time-only dependencies of src/Tracker.py / src/Mapper.py that are absent here (never called by the methods the
+    goldens exercise); cv2, numpy, scipy are the real packages."""
     def stub(name, **attrs):
         if name not in sys.modules:
             m = types.ModuleType(name)
@@ -198,8 +196,31 @@ def load_mapper_class():
     stub('torchmetrics.image')
     stub('torchmetrics.image.lpip', LearnedPerceptualImagePatchSimilarity=object)
     stub('pytorch_msssim', ms_ssim=None)
+    stub('wandb')
+    sk = sys.modules['skimage']
+    if not hasattr(sk.filters, 'sobel_h'):
+        sk.filters.sobel_h = sk.filters.sobel_v = None
+
+
+def load_mapper_class(return_module=False):
+    """The reference `Mapper` class (src/Mapper.py), for its unbound methods (get_mask_from_c2w, optimize_map)."""
+    assert os.path.isdir(REF_ROOT), 'reference tree not present (this harness only runs in the build container)'
+    _install_stubs()
+    _stub_caller_imports()
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     with _cwd(REF_ROOT):
         import src.Mapper as ref_mapper
-    return ref_mapper.Mapper
+    return (ref_mapper.Mapper, ref_mapper) if return_module else ref_mapper.Mapper
+
+
+def load_tracker_class():
+    """The reference `Tracker` class (src/Tracker.py), for its unbound method optimize_cam_in_batch."""
+    assert os.path.isdir(REF_ROOT), 'reference tree not present (this harness only runs in the build container)'
+    _install_stubs()
+    _stub_caller_imports()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    with _cwd(REF_ROOT):
+        import src.Tracker as ref_tracker
+    return ref_tracker.Tracker

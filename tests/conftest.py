@@ -20,3 +20,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU sessions leave the achieved parity errors (case x quantity x error x limit) in profiles/parity_r02.json."""
+    try:
+        from tests.callers import Errors
+    except Exception:
+        return
+    if Errors.rows:
+        Errors.dump(os.path.join(ROOT, 'gpurun_out' if os.environ.get('PSL_PARITY_TO_GPURUN_OUT') else 'profiles', 'parity_r02.json'))
