@@ -249,6 +249,16 @@ int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const floa
                      float* save /* NULL, or the psl_decode_fwd save buffer (FFMA backward) */,
                      float* tsave /* NULL, or psl_tc_save_floats() floats (tensor-core backward) */, psl_stream_t stream);
 
+/* Round-2 forward of the colour branch: operands as f16 hi/lo planes (kind::f16, three MMAs per K = 16 step, same accuracy as
+ * 3xTF32 at twice the MMA rate and half the TMEM / weight bytes) and TWO tiles in flight per CTA (csrc/psl_color_h2.cu).
+ * psl_h2_pack_params builds its operand image (psl_h2_blob_bytes() bytes) from the folded matrices psl_tc_pack_params left in
+ * `tc_blob`; psl_color_fwd_h2 has the contract of psl_color_fwd_tc without the FFMA-layout `save` (tsave or inference only). */
+size_t psl_h2_blob_bytes(void);
+int psl_h2_pack_params(const psl_decoder_params* params_host, const float* tc_blob, void* h2_blob, psl_stream_t stream);
+int psl_color_fwd_h2(const psl_decode_cfg* cfg, const void* h2_blob, const float* pos, int64_t m, const int32_t* I,
+                     const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                     const float* rand_col, const float* exposure_affine, float* raw, float* tsave, psl_stream_t stream);
+
 /* EXPERIMENT, same contract as psl_color_fwd_tc: 16 worker warps (4 threads per sample row, 16-column epilogue chunks) instead
  * of 8 -- csrc/psl_color_tc_w16.cu.  Not on the default path (PSL_W16=1 selects it in ops.py); written after the last GPU
  * session of round 1 and not yet run on hardware. */

@@ -1,0 +1,613 @@
+// Colour branch of the decoder on the 5th-generation tensor cores, round-2 forward:
+//   * operands as 16-bit planes: a = hi + lo with hi = f16(64 a), lo = f16(64 a - hi); three kind::f16 MMAs per K = 16 step
+//     (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM) reproduce the fp32 product as well as 3xTF32 does
+//     (tests/test_gpu_tc.py::test_tc_gemm_f16_planes) at twice the MMA rate, half the weight bytes streamed from L2 and half
+//     the TMEM columns per activation plane (two k per 32-bit column);
+//   * which is what lets TWO 128-sample tiles live in TMEM at once (2 x [D 128 | A hi 64 | A lo 64] = 512 columns): while the
+//     MMAs of one tile run, the 16 worker warps do the other tile's epilogue -- the per-layer hand-offs (tcgen05.commit ->
+//     mbarrier -> tcgen05.ld ... tcgen05.st -> mbarrier) no longer serialise the tile;
+//   * everything else as in psl_color_tc.cu: per-neighbour MLP (52 -> 128 -> 32) with resident weights, trunk (5 x 128 + output)
+//     with fc_c folded into the next layer and its weights streamed through a 4 x 16 KB cp.async.bulk ring, the interpolated
+//     feature c and the Fourier embedding as shared-memory (SS) operands.
+// Scaling: both operands are stored x 64 (keeps the lo planes out of the f16 subnormals for |a| > 4e-3, |a| < 1000 required),
+// the epilogues undo it with one fma (z = D / 4096 + bias).
+// Warp roles: 0-15 workers (thread = sample row r, column quarter q), 16 bulk-copy producer, 17 TMEM allocator + MMA issuer.
+//
+// Replaces (forward) MLP_color.get_feature_at_pos / forward, src/conv_onet/models/decoder.py:341-449.
+#include "psl_color_tc.cuh"
+
+namespace psl {
+namespace ch2 {
+
+using namespace ctc;             // V_* offsets of the small-vector section, TB_VEC, FOLD_LD, l_n, Args
+
+constexpr int NWORKER = 512, NTHREADS = 576;
+constexpr float OP_SCALE = 64.0f, INV_SCALE2 = 1.0f / 4096.0f;
+
+// ---- operand blob (byte offsets) ---------------------------------------------------------------------------------------
+// [vectors (V_SIZE floats, copied from the tf32 blob) | N1 units | N2 units | trunk layers as k-step units]
+// unit = one K = 16 step of an (N x 16) weight slab: [hi plane N*32 B | lo plane N*32 B], canonical 16-bit K-major layout
+__host__ __device__ constexpr int h_ne(int l) { return (l == 0 || l == 3) ? 3 : 0; }     // k-steps fed by the embedding (48 = 40 + pad)
+__host__ __device__ constexpr int h_na(int l) { return l == 0 ? 0 : 8; }                  // k-steps fed by act(z)
+__host__ __device__ constexpr int h_nc(int l) { return l == 0 ? 0 : 2; }                  // k-steps fed by c
+__host__ __device__ constexpr int h_ks(int l) { return h_ne(l) + h_na(l) + h_nc(l); }
+__host__ __device__ constexpr int h_unit(int l) { return l_n(l) * 64; }                   // bytes of one unit
+__host__ __device__ constexpr int h_loff(int l) {
+    int o = 0;
+    for (int i = 0; i < l; ++i) o += h_ks(i) * h_unit(i);
+    return o;
+}
+constexpr int HB_VEC = 0;
+constexpr int HB_N1 = V_SIZE * 4;                     // 4 units of N = 128
+constexpr int HB_N2 = HB_N1 + 4 * 128 * 64;           // 8 units of N = 32
+constexpr int HB_TRUNK = HB_N2 + 8 * 32 * 64;
+constexpr int HB_TOTAL = HB_TRUNK + h_loff(NLAYER);
+static_assert(HB_N1 % 16 == 0 && HB_TRUNK % 16 == 0, "bulk copies need 16-byte alignment");
+
+// ---- shared memory (bytes) ---------------------------------------------------------------------------------------------
+constexpr int NSTAGE = 4, STAGE_BYTES = 16384;
+constexpr int S_NBRW = 0;                              // N1 (32 KB) + N2 (16 KB), resident
+constexpr int S_RING = S_NBRW + 49152;
+constexpr int S_E = S_RING + NSTAGE * STAGE_BYTES;     // per slot: E hi | E lo  (128 x 48 halves each = 12288 B)
+constexpr int S_C = S_E + 2 * 24576;                   // per slot: c hi | c lo  (128 x 32 halves each = 8192 B)
+constexpr int S_IDX = S_C + 2 * 16384;                 // per slot: idx[8][128] int
+constexpr int S_WN = S_IDX + 2 * 4096;                 // per slot: wn[8][128] float
+constexpr int S_POS = S_WN + 2 * 4096;                 // per slot: pos[3][128] float + has[128] float
+constexpr int S_VEC = S_POS + 2 * 2048;
+constexpr int S_RAND = S_VEC + V_SIZE * 4;
+constexpr int S_BAR = S_RAND + 48 * 4;
+constexpr int S_TOTAL = S_BAR + 24 * 8;
+static_assert(S_TOTAL <= 227 * 1024, "shared memory over budget");
+
+// TMEM: slot s at column 256 s: [D 0..127 | A hi 128..191 | A lo 192..255]
+constexpr uint32_t T_D = 0, T_AH = 128, T_AL = 192, T_SLOT = 256;
+
+struct PackArgs { const float* fold; const psl_decoder_params P; unsigned char* hb; const float* vec_src; };
+
+// one thread per (job, row n, k pair): job 0..5 trunk layers (from the fp32 folded rows), 6 = N1, 7 = N2, 8 = vectors
+__global__ void k_h2_pack(PackArgs a) {
+    const int job = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job < NLAYER) {
+        const int l = job, N = l_n(l), K = h_ks(l) * 16;
+        if (e >= N * K / 2) return;
+        const int n = e / (K / 2), k = 2 * (e - n * (K / 2));
+        float w[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int kk = k + t;
+            int col = -1;                                            // column of the folded row [e | act | c]
+            if (l == 0) col = kk < 40 ? kk : -1;
+            else if (l == 3) col = kk < 40 ? kk : (kk < 48 ? -1 : kk - 8);       // e 0..39 | pad | act 40..167 | c 168..199
+            else col = kk;                                           // act 0..127 | c 128..159
+            w[t] = col >= 0 ? a.fold[((size_t)l * 128 + n) * FOLD_LD + col] * OP_SCALE : 0.f;
+        }
+        uint32_t hi, lo;
+        tc::split_h2_f16(w[0], w[1], hi, lo);
+        unsigned char* unit = a.hb + HB_TRUNK + h_loff(l) + (k >> 4) * h_unit(l);
+        const uint32_t o = tc::canon_off_h(n, k & 15, N) * 2;
+        *reinterpret_cast<uint32_t*>(unit + o) = hi;
+        *reinterpret_cast<uint32_t*>(unit + N * 32 + o) = lo;
+    } else if (job == NLAYER) {                                      // N1 (128, 52) -> K = 64
+        if (e >= 128 * 32) return;
+        const int n = e >> 5, k = 2 * (e & 31);
+        uint32_t hi, lo;
+        tc::split_h2_f16(k < 52 ? a.P.c_N1[n * 52 + k] * OP_SCALE : 0.f, k + 1 < 52 ? a.P.c_N1[n * 52 + k + 1] * OP_SCALE : 0.f, hi, lo);
+        unsigned char* unit = a.hb + HB_N1 + (k >> 4) * 128 * 64;
+        const uint32_t o = tc::canon_off_h(n, k & 15, 128) * 2;
+        *reinterpret_cast<uint32_t*>(unit + o) = hi;
+        *reinterpret_cast<uint32_t*>(unit + 128 * 32 + o) = lo;
+    } else if (job == NLAYER + 1) {                                  // N2 (32, 128)
+        if (e >= 32 * 64) return;
+        const int n = e >> 6, k = 2 * (e & 63);
+        uint32_t hi, lo;
+        tc::split_h2_f16(a.P.c_N2[n * 128 + k] * OP_SCALE, a.P.c_N2[n * 128 + k + 1] * OP_SCALE, hi, lo);
+        unsigned char* unit = a.hb + HB_N2 + (k >> 4) * 32 * 64;
+        const uint32_t o = tc::canon_off_h(n, k & 15, 32) * 2;
+        *reinterpret_cast<uint32_t*>(unit + o) = hi;
+        *reinterpret_cast<uint32_t*>(unit + 32 * 32 + o) = lo;
+    } else {
+        if (e < V_SIZE) reinterpret_cast<float*>(a.hb + HB_VEC)[e] = a.vec_src[e];
+    }
+}
+
+// 64 * softplus(beta = 100) = 64 max(x, 0) + 0.64 ln(1 + exp(-100 |x|)): two SFU ops (ex2, lg2) and six FMA-pipe instructions.
+// Above PyTorch's threshold (100 x > 20) the log term is < 2.1e-11, below half an ulp of x: the result rounds to x like nn.Softplus.
+__device__ __forceinline__ float softplus100_x64(float x) {
+    const float t = x * 144.26950408889634f;                    // 100 log2(e)
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return fmaf(l, 0.6931471805599453f * 0.01f * OP_SCALE, fmaxf(x * OP_SCALE, 0.f));
+}
+
+__device__ __forceinline__ void st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// one mbarrier arrival per WARP (512 per-thread arrivals on one shared-memory word serialise: ~1 us per hand-off, 44 per pair)
+__device__ __forceinline__ void signal(uint64_t* a_ready) {
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(a_ready);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int SAVE>
+__global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsigned char* __restrict__ hb, long long n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sVec = reinterpret_cast<float*>(smem + S_VEC);
+    float* sRand = reinterpret_cast<float*>(smem + S_RAND);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_BAR);
+    uint64_t* full = bars;                   // [4]
+    uint64_t* empty = bars + 4;              // [4]
+    uint64_t* nbrw_full = bars + 8;
+    uint64_t* a_ready = bars + 9;            // [2] workers -> MMA (count 16: one arrival per worker warp)
+    uint64_t* d_ready = bars + 11;           // [2] MMA -> workers (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool rel = a.cfg.encode_rel_pos != 0;
+    const TSave TL = tsave_layout(a.m, a.cfg.encode_rel_pos);
+    const long long n_pairs = (n_tiles + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(nbrw_full, 1);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_ready[s], NWORKER / 32); tc::mbar_init(&d_ready[s], 1); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < V_SIZE; i += NTHREADS) sVec[i] = reinterpret_cast<const float*>(hb + HB_VEC)[i];
+    if (threadIdx.x < 32) sRand[threadIdx.x] = a.rand_col[threadIdx.x];
+    if (threadIdx.x < 12) sRand[32 + threadIdx.x] = a.affine ? a.affine[threadIdx.x] : 0.f;
+    // zero the K padding of the embedding operand (k = 40..47 of 48) once: its weights are zero, but 0 x NaN is not
+    for (int i = threadIdx.x; i < 2 * 2 * 128; i += NTHREADS) {
+        const int s = i >> 8, plane = (i >> 7) & 1, r = i & 127;
+        *reinterpret_cast<uint4*>(smem + S_E + s * 24576 + plane * 12288 + tc::canon_off_h(r, 40, 128) * 2) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // =============================== bulk-copy producer ==========================================================
+        if (lane == 0) {
+            if (rel) {
+                tc::mbar_expect_tx(nbrw_full, 49152);
+                for (int i = 0; i < 3; ++i) tc::bulk_g2s(smem + S_NBRW + i * 16384, hb + HB_N1 + i * 16384, 16384, nbrw_full);
+            }
+            uint32_t cnt = 0;
+            for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
+                for (int l = 0; l < NLAYER; ++l) {
+                    const int ks = h_ks(l), ub = h_unit(l);
+                    for (int s = 0; s < ns; ++s)
+                        for (int j = 0; j < ks; j += 2, ++cnt) {
+                            const int st = cnt & (NSTAGE - 1);
+                            const uint32_t bytes = (uint32_t)(min(2, ks - j) * ub);
+                            tc::mbar_wait_p(&empty[st], ((cnt / NSTAGE) & 1) ^ 1);
+                            tc::mbar_expect_tx(&full[st], bytes);
+                            tc::bulk_g2s(smem + S_RING + st * STAGE_BYTES, hb + HB_TRUNK + h_loff(l) + j * ub, bytes, &full[st]);
+                        }
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // =============================== MMA issuer (one thread) ======================================================
+        if (lane == 0) {
+            uint32_t pa[2] = {0, 0}, cnt = 0;
+            const uint32_t n1 = tc::smem_u32(smem + S_NBRW), n2 = n1 + 32768;
+            const uint32_t id128 = tc::make_idesc_f16(128, 128, tc::FMT_F16, tc::FMT_F16);
+            const uint32_t id32 = tc::make_idesc_f16(128, 32, tc::FMT_F16, tc::FMT_F16);
+            const uint32_t id16 = tc::make_idesc_f16(128, 16, tc::FMT_F16, tc::FMT_F16);
+            if (rel) tc::mbar_wait_p(nbrw_full, 0);
+            for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
+                if (rel) {
+                    for (int k = 0; k < 8; ++k) {
+                        for (int s = 0; s < ns; ++s) {               // z1 = x N1^T   (K = 64, N = 128)
+                            const uint32_t ts = tmem + T_SLOT * s;
+                            tc::mbar_wait_p(&a_ready[s], pa[s]); pa[s] ^= 1; tc::fence_after_sync();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint64_t bh = tc::make_smem_desc(n1 + j * 8192, 2048, 128);
+                                const uint64_t bl = tc::make_smem_desc(n1 + j * 8192 + 4096, 2048, 128);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + 8 * j, bh, id128, j > 0);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AL + 8 * j, bh, id128, 1);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + 8 * j, bl, id128, 1);
+                            }
+                            tc::mma_commit(&d_ready[s]);
+                        }
+                        for (int s = 0; s < ns; ++s) {               // f = softplus(z1) N2^T   (K = 128, N = 32)
+                            const uint32_t ts = tmem + T_SLOT * s;
+                            tc::mbar_wait_p(&a_ready[s], pa[s]); pa[s] ^= 1; tc::fence_after_sync();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint64_t bh = tc::make_smem_desc(n2 + j * 2048, 512, 128);
+                                const uint64_t bl = tc::make_smem_desc(n2 + j * 2048 + 1024, 512, 128);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + 8 * j, bh, id32, j > 0);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AL + 8 * j, bh, id32, 1);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + 8 * j, bl, id32, 1);
+                            }
+                            tc::mma_commit(&d_ready[s]);
+                        }
+                    }
+                }
+                for (int l = 0; l < NLAYER; ++l) {
+                    const int N = l_n(l), ks = h_ks(l), ne = h_ne(l), na = h_na(l);
+                    const uint32_t idesc = l == 5 ? id16 : id128;
+                    const uint32_t lbo = (uint32_t)N * 16u, ub16 = (uint32_t)h_unit(l) >> 4;
+                    const uint32_t hi128 = tc::desc_hi(128);
+                    for (int s = 0; s < ns; ++s) {
+                        const uint32_t ts = tmem + T_SLOT * s;
+                        // descriptor low words: B (ring stage 0, unit 0), A operands in shared memory (embedding / c planes of slot s)
+                        const uint32_t b0 = tc::desc_lo(tc::smem_u32(smem + S_RING), lbo);
+                        const uint32_t e0 = tc::desc_lo(tc::smem_u32(smem + S_E + s * 24576), 2048);
+                        const uint32_t c0 = tc::desc_lo(tc::smem_u32(smem + S_C + s * 16384), 2048);
+                        tc::mbar_wait_p(&a_ready[s], pa[s]); pa[s] ^= 1; tc::fence_after_sync();
+                        for (int j = 0; j < ks; ++j) {
+                            const int u = j & 1;
+                            const int st = cnt & (NSTAGE - 1);
+                            if (u == 0) { tc::mbar_wait_p(&full[st], (cnt / NSTAGE) & 1); tc::fence_after_sync(); }
+                            const uint32_t bl_ = b0 + (uint32_t)st * (STAGE_BYTES >> 4) + (uint32_t)u * ub16;
+                            const uint64_t bh = tc::desc_of(bl_, hi128), bl = tc::desc_of(bl_ + (ub16 >> 1), hi128);
+                            const uint32_t acc = j > 0;
+                            if (j < ne || j >= ne + na) {            // embedding / interpolated feature: A from shared memory
+                                const uint32_t a_ = (j < ne ? e0 + (uint32_t)j * 256u : c0 + (uint32_t)(j - ne - na) * 256u);
+                                const uint64_t ah = tc::desc_of(a_, hi128), al = tc::desc_of(a_ + (j < ne ? 768u : 512u), hi128);
+                                tc::mma_f16_ss(ts + T_D, ah, bh, idesc, acc);
+                                tc::mma_f16_ss(ts + T_D, al, bh, idesc, 1);
+                                tc::mma_f16_ss(ts + T_D, ah, bl, idesc, 1);
+                            } else {                                 // act(z): A planes resident in TMEM
+                                const uint32_t c = 8 * (j - ne);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + c, bh, idesc, acc);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AL + c, bh, idesc, 1);
+                                tc::mma_f16_ts(ts + T_D, ts + T_AH + c, bl, idesc, 1);
+                            }
+                            if (u == 1 || j == ks - 1) { tc::mma_commit(&empty[st]); ++cnt; }
+                        }
+                        tc::mma_commit(&d_ready[s]);
+                    }
+                }
+            }
+        }
+    } else {
+        // =============================== workers: thread = (sample row r, column quarter q) =============================
+        const int r = 32 * (warp & 3) + lane, q = warp >> 2;
+        const uint32_t lb = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        uint32_t pd[2] = {0, 0};
+        const float* b1 = sVec + V_B1; const float* b2 = sVec + V_B2; const float* Bc = sVec + V_BC; const float* Br = sVec + V_BREL;
+        int* sIdx = reinterpret_cast<int*>(smem + S_IDX);
+        float* sWn = reinterpret_cast<float*>(smem + S_WN);
+        float* sPos = reinterpret_cast<float*>(smem + S_POS);
+
+        // x_k of slot s, neighbour k -> A planes (this thread: 16 of the 64 K columns)
+        //   [sin(10) | cos(10) | col_feats[I_k](32) | 0(12)]; quarter 0: sin 0-9, cos 0-5; 1: cos 6-9, feat 0-11; 2: feat 12-27; 3: feat 28-31
+        // Two halves: load_x issues the gathers (neighbour position for quarters 0-1, this quarter's feature columns), finish_x turns them
+        // into the operand.  The caller puts an mbarrier wait between the two, so the L2 / HBM latency of the gathers is spent waiting
+        // for MMAs that have to finish anyway.
+        auto load_x = [&](int s, int k, float (&raw)[16]) -> int {
+            const int id = sIdx[(s * 8 + k) * 128 + r];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) raw[j] = 0.f;
+            if (id >= 0) {
+                if (q < 2) {
+                    raw[0] = __ldg(a.cloud_pos + (size_t)id * 3); raw[1] = __ldg(a.cloud_pos + (size_t)id * 3 + 1);
+                    raw[2] = __ldg(a.cloud_pos + (size_t)id * 3 + 2);
+                }
+                const float4* f = reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32);
+                if (q == 1) {
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) { const float4 v = __ldg(f + g); raw[4 + 4 * g] = v.x; raw[5 + 4 * g] = v.y; raw[6 + 4 * g] = v.z; raw[7 + 4 * g] = v.w; }
+                } else if (q == 2) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { const float4 v = __ldg(f + 3 + g); raw[4 * g] = v.x; raw[4 * g + 1] = v.y; raw[4 * g + 2] = v.z; raw[4 * g + 3] = v.w; }
+                } else if (q == 3) {
+                    const float4 v = __ldg(f + 7); raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+                }
+            }
+            if (k < 7) {                                     // the neighbour after this one: towards L2 a whole step ahead
+                const int idn = sIdx[(s * 8 + k + 1) * 128 + r];
+                if (idn >= 0) {
+                    if (q > 0) prefetch_l2(a.col_feats + (size_t)idn * 32);
+                    if (q < 2) prefetch_l2(a.cloud_pos + (size_t)idn * 3);
+                }
+            }
+            return id;
+        };
+        auto finish_x = [&](int s, int id, float (&raw)[16]) {
+            if (q < 2) {
+                float rx = 0.f, ry = 0.f, rz = 0.f;
+                if (id >= 0) {
+                    rx = __fmul_rn(kTwoPi, __fsub_rn(raw[0], sPos[(s * 4 + 0) * 128 + r]));
+                    ry = __fmul_rn(kTwoPi, __fsub_rn(raw[1], sPos[(s * 4 + 1) * 128 + r]));
+                    rz = __fmul_rn(kTwoPi, __fsub_rn(raw[2], sPos[(s * 4 + 2) * 128 + r]));
+                }
+                if (q == 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 10; ++jj) {
+                        float sn = 0.f, cs = 0.f;
+                        if (id >= 0) sincos_embed(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
+                        raw[jj] = sn;
+                        if (jj < 6) raw[10 + jj] = cs;
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 6; jj < 10; ++jj) {
+                        float sn = 0.f, cs = 0.f;
+                        if (id >= 0) sincos_embed(fmaf(rz, Br[24 + jj], fmaf(ry, Br[12 + jj], rx * Br[jj])), &sn, &cs);
+                        raw[jj - 6] = cs;
+                    }
+                }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split_h2_f16(raw[2 * j] * OP_SCALE, raw[2 * j + 1] * OP_SCALE, hi[j], lo[j]);
+            const uint32_t ts = lb + T_SLOT * s;
+            st8u(ts + T_AH + 8 * q, hi);
+            st8u(ts + T_AL + 8 * q, lo);
+        };
+
+        // 32 columns (32 q .. 32 q + 31) of a 128-wide pre-activation: z = D / 4096 + bias, saved, softplus, f16 planes -> A region
+        auto epilogue128 = [&](int s, const float* bias, float* save_base /* [channel][128 samples] tile block or nullptr */) {
+            const uint32_t ts = lb + T_SLOT * s;
+            const int c0 = 32 * q;
+            float v[32];
+            {   // both 16-column loads in flight before the first value is used
+                uint32_t r0[16], r1[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+                      "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                    : "r"(ts + T_D + c0) : "memory");
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                      "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                    : "r"(ts + T_D + c0 + 16) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], INV_SCALE2, bias[c0 + j]);
+            if (SAVE == 2) {
+                float* dst = save_base + (size_t)c0 * 128 + r;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[j * 128] = v[j];
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    tc::split_h2_f16(softplus100_x64(v[16 * c + 2 * j]), softplus100_x64(v[16 * c + 2 * j + 1]), hi[j], lo[j]);
+                st8u(ts + T_AH + c0 / 2 + 8 * c, hi);
+                st8u(ts + T_AL + c0 / 2 + 8 * c, lo);
+            }
+        };
+
+        for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
+            bool inb[2], has[2];
+            float cacc[2][8];
+            // ---- per-row state of the pair's tiles -> shared memory (quarter 0 computes the IDW weights once per row)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const long long m = (2 * pair + s) * TM + r;
+                inb[s] = s < ns && m < a.m;
+                has[s] = false;
+                if (inb[s]) has[s] = a.nnum[m] >= a.cfg.min_nn;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cacc[s][j] = 0.f;
+                if (q == 0 && s < ns) {
+                    float px = 0.f, py = 0.f, pz = 0.f, w[8], sum = 0.f, tle = -1.f;
+                    int idx[8];
+                    if (inb[s]) {
+                        px = a.pos[m * 3]; py = a.pos[m * 3 + 1]; pz = a.pos[m * 3 + 2];
+                        tle = thr_le_of(a.r2 ? a.r2[m / a.cfg.r2_group] : a.cfg.r2_scalar);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        idx[k] = inb[s] ? a.I[m * 8 + k] : -1;
+                        w[k] = inb[s] ? idw_raw(a.D[m * 8 + k], idx[k], tle, a.cfg.weighting) : 0.f;
+                        sum += fabsf(w[k]);
+                    }
+                    const float den = fmaxf(sum, 1e-12f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float wn = __fdiv_rn(w[k], den);
+                        sWn[(s * 8 + k) * 128 + r] = wn;
+                        sIdx[(s * 8 + k) * 128 + r] = w[k] == 0.f ? -1 : idx[k];
+                        if (SAVE == 2) a.tsave[TL.wnT + ((2 * pair + s) * 8 + k) * 128 + r] = wn;
+                    }
+                    sPos[(s * 4 + 0) * 128 + r] = px; sPos[(s * 4 + 1) * 128 + r] = py; sPos[(s * 4 + 2) * 128 + r] = pz;
+                }
+            }
+            worker_bar();
+
+            if (rel) {
+                for (int s = 0; s < ns; ++s) {
+                    float raw[16];
+                    const int id = load_x(s, 0, raw);
+                    finish_x(s, id, raw);
+                    signal(&a_ready[s]);
+                }
+#pragma unroll 1
+                for (int k = 0; k < 8; ++k) {
+                    // ---- z1 + b1 -> softplus -> planes
+                    for (int s = 0; s < ns; ++s) {
+                        tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
+                        epilogue128(s, b1, SAVE == 2 ? a.tsave + TL.z1T + (((2 * pair + s) * 8 + k) * 128) * 128 : nullptr);
+                        signal(&a_ready[s]);
+                    }
+                    // ---- f = D2 / 4096 + b2 ; c += wn_k f ; then the next neighbour's x (or, after the last one, c and the embedding)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        if (s >= ns) break;
+                        float raw[16];
+                        int idn = -1;
+                        if (k < 7) idn = load_x(s, k + 1, raw);          // gathers of the next neighbour in flight across the wait
+                        tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
+                        float f[8];
+                        tc::tmem_ld8(lb + T_SLOT * s + T_D + 8 * q, f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], INV_SCALE2, b2[8 * q + j]);
+                        if (SAVE == 2) {
+                            float4* dst = reinterpret_cast<float4*>(a.tsave + TL.f + (((2 * pair + s) * 128 + r) * 8 + k) * 32 + 8 * q);
+                            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                        const float wn = sWn[(s * 8 + k) * 128 + r];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cacc[s][j] = fmaf(wn, f[j], cacc[s][j]);
+                        if (k < 7) { finish_x(s, idn, raw); signal(&a_ready[s]); }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s >= ns) break;
+#pragma unroll 1
+                    for (int k = 0; k < 8; ++k) {
+                        const int id = sIdx[(s * 8 + k) * 128 + r];
+                        if (id < 0) continue;
+                        const float wn = sWn[(s * 8 + k) * 128 + r];
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const float4 f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32 + 8 * q) + g);
+                            cacc[s][4 * g] = fmaf(wn, f4.x, cacc[s][4 * g]); cacc[s][4 * g + 1] = fmaf(wn, f4.y, cacc[s][4 * g + 1]);
+                            cacc[s][4 * g + 2] = fmaf(wn, f4.z, cacc[s][4 * g + 2]); cacc[s][4 * g + 3] = fmaf(wn, f4.w, cacc[s][4 * g + 3]);
+                        }
+                    }
+                }
+            }
+            // ---- c (planes) and the colour embedding (planes) -> shared-memory A operands of the trunk
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s >= ns) break;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cacc[s][j] = has[s] ? cacc[s][j] : sRand[8 * q + j];
+                if (SAVE == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a.tsave[TL.cT + ((2 * pair + s) * 32 + 8 * q + j) * 128 + r] = cacc[s][j];
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc::split_h2_f16(cacc[s][2 * j] * OP_SCALE, cacc[s][2 * j + 1] * OP_SCALE, hi[j], lo[j]);
+                unsigned char* cp = smem + S_C + s * 16384 + tc::canon_off_h(r, 8 * q, 128) * 2;        // k = 8q..8q+7: one core-matrix row
+                *reinterpret_cast<uint4*>(cp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(cp + 8192) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                // embedding columns [sin 0-19 | cos 0-19]; quarter 0: sin 0-9, 1: sin 10-19, 2: cos 0-9, 3: cos 10-19
+                const float x = __fmul_rn(kTwoPi, sPos[(s * 4 + 0) * 128 + r]), y = __fmul_rn(kTwoPi, sPos[(s * 4 + 1) * 128 + r]),
+                            z = __fmul_rn(kTwoPi, sPos[(s * 4 + 2) * 128 + r]);
+                const int j0 = 10 * (q & 1), col0 = 20 * (q >> 1) + j0;
+                unsigned char* ep = smem + S_E + s * 24576;
+#pragma unroll 2
+                for (int j = 0; j < 10; j += 2) {
+                    const float a0 = fmaf(z, Bc[40 + j0 + j], fmaf(y, Bc[20 + j0 + j], x * Bc[j0 + j]));
+                    const float a1 = fmaf(z, Bc[41 + j0 + j], fmaf(y, Bc[21 + j0 + j], x * Bc[j0 + j + 1]));
+                    uint32_t eh, el;
+                    tc::split_h2_f16((q < 2 ? sin_embed(a0) : cos_embed(a0)) * OP_SCALE, (q < 2 ? sin_embed(a1) : cos_embed(a1)) * OP_SCALE, eh, el);
+                    const uint32_t o = tc::canon_off_h(r, col0 + j, 128) * 2;              // col0 + j is even: the pair shares a word
+                    *reinterpret_cast<uint32_t*>(ep + o) = eh;
+                    *reinterpret_cast<uint32_t*>(ep + 12288 + o) = el;
+                }
+                tc::fence_proxy_async();
+                signal(&a_ready[s]);
+            }
+            // ---- trunk epilogues
+#pragma unroll 1
+            for (int l = 0; l < 5; ++l) {
+                for (int s = 0; s < ns; ++s) {
+                    tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
+                    epilogue128(s, sVec + V_BIAS + 128 * l,
+                                SAVE == 2 ? a.tsave + TL.zT + (((long long)l * n_tiles + (2 * pair + s)) * 128) * 128 : nullptr);
+                    signal(&a_ready[s]);
+                }
+            }
+            // ---- output layer (quarter 0 writes the pixel)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s >= ns) break;
+                tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
+                if (q == 0) {
+                    float o[8];
+                    tc::tmem_ld8(lb + T_SLOT * s + T_D, o);
+                    if (inb[s]) {
+                        const long long m = (2 * pair + s) * TM + r;
+                        float cr = fmaf(o[0], INV_SCALE2, sVec[V_BOUT]), cg = fmaf(o[1], INV_SCALE2, sVec[V_BOUT + 1]),
+                              cb = fmaf(o[2], INV_SCALE2, sVec[V_BOUT + 2]);
+                        if (SAVE == 2) *reinterpret_cast<float4*>(a.tsave + TL.outpre + ((2 * pair + s) * 128 + r) * 4) = make_float4(cr, cg, cb, 0.f);
+                        if (a.cfg.rgb_mode == PSL_RGB_AFFINE_SIGMOID) {
+                            const float* A = sRand + 32;
+                            const float r2 = fmaf(cb, A[6], fmaf(cg, A[3], cr * A[0])) + A[9];
+                            const float g2 = fmaf(cb, A[7], fmaf(cg, A[4], cr * A[1])) + A[10];
+                            const float b2_ = fmaf(cb, A[8], fmaf(cg, A[5], cr * A[2])) + A[11];
+                            cr = r2; cg = g2; cb = b2_;
+                        }
+                        if (a.cfg.rgb_mode != PSL_RGB_RAW) { cr = sigmoidf_(cr); cg = sigmoidf_(cg); cb = sigmoidf_(cb); }
+                        a.raw[m * 4] = cr; a.raw[m * 4 + 1] = cg; a.raw[m * 4 + 2] = cb;
+                    }
+                }
+            }
+            worker_bar();          // the next pair's setup overwrites the per-row state the slower warps may still be reading
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 17) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace ch2
+}  // namespace psl
+
+using namespace psl;
+
+extern "C" size_t psl_h2_blob_bytes(void) { return (size_t)ch2::HB_TOTAL; }
+
+// f16 hi/lo operand images of the colour branch from the folded fp32 matrices psl_tc_pack_params leaves behind its blob
+extern "C" int psl_h2_pack_params(const psl_decoder_params* P, const float* tc_blob, void* h2_blob, psl_stream_t stream) {
+    PSL_REQUIRE(P && tc_blob && h2_blob, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    ch2::PackArgs pa{tc_blob + ctc::TB_TOTAL, *P, static_cast<unsigned char*>(h2_blob), tc_blob + ctc::TB_VEC};
+    TimingScope ts(T_PACK, st);
+    ch2::k_h2_pack<<<dim3((128 * 104 + 255) / 256, ctc::NLAYER + 3), 256, 0, st>>>(pa);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// colour branch on tensor cores (f16 hi/lo planes, two tiles in flight): writes raw[:, 0:3]; raw[:, 3] / has_nb come from
+// psl_decode_fwd(stage = geometry).  tsave: NULL (inference) or the psl_tc_save_floats() buffer of the tensor-core backward.
+extern "C" int psl_color_fwd_h2(const psl_decode_cfg* cfg, const void* h2_blob, const float* pos, int64_t m, const int32_t* I,
+                                const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                                const float* rand_col, const float* exposure_affine, float* raw, float* tsave, psl_stream_t stream) {
+    PSL_REQUIRE(cfg && h2_blob && pos && I && D && nnum && col_feats && rand_col && raw, "NULL argument");
+    PSL_REQUIRE(!cfg->encode_rel_pos || cloud_pos, "rel-pos encoding needs cloud_pos");
+    PSL_REQUIRE(cfg->rgb_mode != PSL_RGB_AFFINE_SIGMOID || exposure_affine, "affine mode needs exposure_affine");
+    if (m == 0) return 0;
+    ctc::Args a{};
+    a.cfg = *cfg; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
+    a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.tsave = tsave;
+    const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
+    const long long n_pairs = (n_tiles + 1) / 2;
+    int dev = 0;
+    PSL_CHECK_CUDA(cudaGetDevice(&dev));
+    static bool attr_set[64] = {};
+    if (dev < 64 && !attr_set[dev]) {
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
+        PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
+        attr_set[dev] = true;
+    }
+    const long long grid = n_pairs < sm_count() ? n_pairs : sm_count();
+    TimingScope ts(T_COLOR_FWD_TC, as_stream(stream));
+    const unsigned char* hb = static_cast<const unsigned char*>(h2_blob);
+    if (tsave) ch2::k_color_fwd_h2<2><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles);
+    else ch2::k_color_fwd_h2<0><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

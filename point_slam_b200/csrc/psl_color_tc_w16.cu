@@ -22,7 +22,8 @@ using tc::mbar_wait_wd;
 __device__ __forceinline__ void worker_signal16(uint64_t* a_ready) {
     tc::tmem_st_wait();
     tc::fence_before_sync();
-    tc::mbar_arrive(a_ready);
+    __syncwarp();                                    // one arrival per warp: 512 per-thread arrivals on one word serialise
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(a_ready);
 }
 
 template <int SAVE>
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(NTHR16, 1) k_color_fwd_tc_w16(Args a, long lon
         tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
         tc::mbar_init(&empty[0], 1); tc::mbar_init(&empty[1], 1);
         tc::mbar_init(nbrw_full, 1);
-        tc::mbar_init(a_ready, NWORK16);
+        tc::mbar_init(a_ready, NWORK16 / 32);
         tc::mbar_init(d_ready, 1);
         tc::mbar_fence_init();
     }

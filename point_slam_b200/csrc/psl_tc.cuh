@@ -214,6 +214,19 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     for (uint32_t n = 1; !mbar_try(bar, parity); ++n)
         if ((n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
 }
+// the wait the production kernels use: the bare try_wait loop (the instruction itself suspends the warp up to a hardware time
+// limit, so a waiting warp costs two issue slots per wake-up); -DPSL_WATCHDOG turns every wait into the trapping variant
+__device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity) {
+#ifdef PSL_WATCHDOG
+    mbar_wait_wd(bar, parity);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+// shared-memory descriptor as two words: lo = start>>4 | LBO>>4 << 16 (add byte_offset >> 4 to move the start), hi = SBO>>4 | 1 << 14
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3fffu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 // global -> shared 1-D bulk copy (bytes multiple of 16, both addresses 16 B aligned); completes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -238,6 +238,7 @@ USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-b
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
 USE_W16_FORWARD = os.environ.get('PSL_W16', '1') == '1'       # 16-worker-warp colour forward (psl_color_tc_w16.cu); bit-identical to the 8-warp kernel, 11 % faster (profiles/r02_s1)
 USE_W16_BACKWARD = os.environ.get('PSL_W16', '1') == '1'      # 16-worker-warp colour backward (psl_color_bwd_tc_w16.cu); bit-identical, 14 % faster
+USE_H2_FORWARD = os.environ.get('PSL_H2', '1') != '0'           # f16-plane, two-tiles-in-flight colour forward (psl_color_h2.cu)
 OVERLAP_BRANCHES = os.environ.get('PSL_OVERLAP', '1') != '0'  # geometry kernel on a forked stream next to the colour kernel
 _SIDE = {}
 
@@ -259,12 +260,14 @@ class PackedDecoder:
         self.packed = torch.empty(lib.psl_packed_params_floats(), dtype=torch.float32, device=device)
         self.blob = torch.empty(lib.psl_tc_blob_floats(), dtype=torch.float32, device=device)
         self.bblob = torch.empty(lib.psl_tc_bwd_blob_floats(), dtype=torch.float32, device=device)
+        self.hblob = torch.empty(lib.psl_h2_blob_bytes(), dtype=torch.uint8, device=device)      # f16 hi/lo planes (psl_color_h2.cu)
 
     def pack(self, params, backward=True):
         lib = L.load()
         pstruct = _param_struct([_f32c(p.detach()) for p in params])
         L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(self.packed), L.stream()), 'psl_pack_params')
         L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(self.blob), L.stream()), 'psl_tc_pack_params')
+        L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(self.blob), L.ptr(self.hblob), L.stream()), 'psl_h2_pack_params')
         if backward:
             L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(self.blob), lib.psl_tc_fold_offset_floats(), L.ptr(self.bblob),
                                                L.stream()), 'psl_tc_bwd_pack_params')
@@ -312,16 +315,24 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 1, cfg.r2_scalar)       # reserved bit 0: occupancy only, rgb belongs to the colour kernel
         blob = pk.blob
+        use_h2 = USE_H2_FORWARD and (tc_bwd or not need_grad)
         if not prepacked:
             L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+            if use_h2:
+                L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(blob), L.ptr(pk.hblob), L.stream()), 'psl_h2_pack_params')
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if OVERLAP_BRANCHES else None
         if side is not None:
             side.wait_stream(main)                       # fork: everything issued so far (kNN, packing) is visible to the side stream
-        fwd_tc = lib.psl_color_fwd_tc_w16 if USE_W16_FORWARD else lib.psl_color_fwd_tc
-        L.check(fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
-                       L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
-                       None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
+        if use_h2:
+            L.check(lib.psl_color_fwd_h2(C.byref(cfg), L.ptr(pk.hblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                                         L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.ptr(tsave),
+                                         L.stream()), 'psl_color_fwd_h2')
+        else:
+            fwd_tc = lib.psl_color_fwd_tc_w16 if USE_W16_FORWARD else lib.psl_color_fwd_tc
+            L.check(fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+                           L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
+                           None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
             L.check(lib.psl_decode_fwd(C.byref(gcfg), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                                        L.ptr(cloud_pos), L.ptr(geo), None, L.ptr(rand_geo), None, None, L.ptr(raw),
