@@ -52,6 +52,9 @@ CONFIGS = {
                name='C4 TUM-fr1_desk-like tracking only'),
     'c1': dict(mode='render', dataset='replica', points=50000, S=5, rays=1000, name='C1 single-batch render'),
     'c3': dict(mode='render', dataset='replica', points=2000000, S=32, rays=5000, name='C3 2M-point cloud, MLP-decode roofline'),
+    # end-of-run re-render (Mapper.py:826-876): one step = FRAMES_PER_STEP full 640x480 images from their poses, frames sharded over the
+    # ranks (frame r, r + N, ...) against the replicated cloud -> STRONG scaling (fixed total work); one all_reduce of the metrics per step
+    'rerender': dict(mode='rerender', dataset='replica', points=500000, S=5, frames=8, name='frame-parallel re-render of 8 full 640x480 frames'),
 }
 
 
@@ -66,6 +69,9 @@ def workload_config(name, points):
     if c['mode'] == 'render':
         return {'workload': f"{c['name']}: {c['rays']} rays x {c['S']} samples, {points} pts, forward render (kNN + decode + composite)",
                 'points': points, 'rays': c['rays'], 'S': c['S'], 'parallelism': 'scene-per-gpu'}
+    if c['mode'] == 'rerender':
+        return {'workload': f"{c['name']} (render_img: 307200 rays x {c['S']} samples each), {points} pts, frames sharded over the GPUs",
+                'points': points, 'frames_per_step': c['frames'], 'S': c['S'], 'parallelism': 'frame-parallel'}
     w = f"{c['name']}: {c['track'][0]} track it x {c['track'][1]} rays"
     mix = {'track_iters': c['track'][0], 'track_rays': c['track'][1]}
     if c['map']:
@@ -347,6 +353,50 @@ class RenderScene:
                                            (b['r_query'] ** 2).contiguous())
 
 
+class RerenderScene:
+    """Frame-parallel re-render: the cloud / features / decoders are replicated (same seed on every rank), the frames of a step
+    are sharded over the ranks by parallel.rerender_frames."""
+
+    def __init__(self, rank, world, device, wl, n_points, n_frames):
+        from point_slam_b200.src.utils.Renderer import Renderer
+        import types
+        self.device, self.wl, self.S, self.world = device, wl, wl['S'], world
+        self.cfg = make_cfg(wl['dataset'], device)
+        self.decoders = build_decoders(self.cfg, device)
+        self.npc = build_cloud(self.cfg, device, n_points, 1219)
+        self.renderer = Renderer(self.cfg, None, types.SimpleNamespace(**{k: INTR[k] for k in ('H', 'W', 'fx', 'fy', 'cx', 'cy')}))
+        self.renderer.sigmoid_coefficient = 0.1
+        F = wl['frames']
+        host = make_frames(F, seed=1219)
+        self.pinned = [{k: torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory() for k in ('color', 'depth', 'dyn_r_query')} for f in host]
+        self.c2w = [torch.from_numpy(f['c2w']).float().to(device) for f in host]
+        self.resident = [dict(color=p['color'].to(device), depth=p['depth'].to(device), dyn_r_query=p['dyn_r_query'].to(device), c2w=c)
+                         for p, c in zip(self.pinned, self.c2w)]
+        self.stage = [{k: torch.empty_like(v) for k, v in f.items()} for f in self.resident]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned[0].values()) * F
+        self.out_host = torch.empty(4, dtype=torch.float64).pin_memory()
+        self.tracker = self.mapper = None
+        self.metrics = None
+
+    def step(self, k, from_host, graphs=True):
+        from point_slam_b200 import parallel as PAR
+        frames = self.resident
+        if from_host:
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            for i in PAR.shard_strided(len(self.stage), rank, self.world):        # only this rank's frames cross the bus
+                for key, t in self.pinned[i].items():
+                    self.stage[i][key].copy_(t, non_blocking=True)
+                self.stage[i]['c2w'] = self.c2w[i]
+            frames = self.stage
+        self.metrics = PAR.rerender_frames(self.renderer, self.npc, self.decoders, frames, self.device)
+        n_local = len(self.metrics['rendered'])
+        return n_local * INTR['H'] * INTR['W'] * self.S
+
+    def captures(self):
+        return 0
+
+
 def timed_steps(scene, steps, first, from_host, dist):
     torch.cuda.synchronize()
     if dist is not None:
@@ -383,9 +433,11 @@ def run_ours(args):
     lib = _lib.load()
     wl = CONFIGS[args.config]
     points = args.points or wl['points']
-    render_mode = wl['mode'] == 'render'
+    render_mode = wl['mode'] in ('render', 'rerender')
     n_frames = args.steps + args.warmup
-    if render_mode:
+    if wl['mode'] == 'rerender':
+        scene = RerenderScene(rank, world, device, wl, points, n_frames)
+    elif render_mode:
         scene = RenderScene(rank, device, wl, points, n_frames)
     else:
         scene = GpuScene(rank, device, wl, points, n_frames, share_map=args.share_map and world > 1, dist=dist)
@@ -407,7 +459,7 @@ def run_ours(args):
     l0 = lib.psl_launch_count()
     overlap, _ops.OVERLAP_BRANCHES = _ops.OVERLAP_BRANCHES, False
     _lib.timing_enable(True)
-    n_prof = scene.step(args.warmup, False, graphs=False)
+    n_prof = scene.step(min(args.warmup, n_frames - 1), False, graphs=False)
     prof = _lib.timing_collect()
     _lib.timing_enable(False)
     _ops.OVERLAP_BRANCHES = overlap
@@ -483,14 +535,16 @@ def run_ours(args):
     out = {
         'metric': 'ray-samples/sec (render+kNN+MLP' + (' forward' if render_mode else ' fwd+bwd, frame step') + ')', 'value': value,
         'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-        'frames_per_sec': world * args.steps / (ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'frames_per_sec': (wl['frames'] if wl['mode'] == 'rerender' else world) * args.steps / (ms * 1e-3), 'higher_is_better': True,
+        'scaling': 'strong' if wl['mode'] == 'rerender' else 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
         'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
                    'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms,
                    'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0)},
         'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes,
-                'd2h_bytes_per_step': 32 if not render_mode else scene.out_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': 32 if not render_mode else scene.out_host.numel() * scene.out_host.element_size(),
+                'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': roof,
@@ -498,7 +552,10 @@ def run_ours(args):
         'kernel_ms_per_step': {k: round(v[0], 3) for k, v in prof.items()},
         'kernel_launches_per_step': {k: v[1] for k, v in prof.items()},
     }
-    if render_mode:
+    if wl['mode'] == 'rerender':
+        out['rerender'] = {k: v for k, v in scene.metrics.items() if k != 'rendered'}
+        cfg_out['parallelism'] = f'frame-parallel x{world} (cloud replicated; one all_reduce of the image metrics per step)'
+    if wl['mode'] == 'render':
         out['knn'] = scene.knn_stats()
         knn_ms = prof['knn'][0]
         out['value_knn_excluded'] = n_prof / max((tot_kernel_ms - knn_ms) * 1e-3, 1e-9)
@@ -625,7 +682,7 @@ def cpu_sample_sizes(name):
     """Bounded CPU sample of one step with the SAME iteration mix as the CUDA arm (track : map iterations and the geometry
     share of the mapping iterations), sized for ~10-20 s on the host cores."""
     wl = CONFIGS[name]
-    if wl['mode'] == 'render':
+    if wl['mode'] in ('render', 'rerender'):
         return None
     if wl['map']:
         f = 5                                               # c2: 40 : 60 (25 geometry) -> 8 : 12 (5 geometry)
@@ -651,7 +708,8 @@ def pick_threads(step_fn):
 def cpu_run(name, n_points, steps, warmup):
     """-> (samples/s, threads, seconds, description of the per-step sample)"""
     wl = CONFIGS[name]
-    if wl['mode'] == 'render':
+    if wl['mode'] in ('render', 'rerender'):
+        wl = dict(wl, rays=wl.get('rays', 2000))           # re-render: a 2000-ray sample of the image
         sc = CpuRenderScene(wl, n_points, steps + warmup + 2)
         n_rays = min(wl['rays'], 1000)
         threads = pick_threads(lambda k: sc.step(k, 200))
@@ -660,7 +718,8 @@ def cpu_run(name, n_points, steps, warmup):
         t0 = time.perf_counter()
         n = sum(sc.step(2 + warmup + k, n_rays) for k in range(steps))
         dt = time.perf_counter() - t0
-        return n / dt, threads, dt, f'{n_rays} of the {wl["rays"]} rays x {wl["S"]} samples, forward render'
+        what = f'{n_rays} of the {wl["rays"]} rays' if CONFIGS[name]['mode'] == 'render' else f'{n_rays} rays of a 640x480 frame'
+        return n / dt, threads, dt, f'{what} x {wl["S"]} samples, forward render'
     r_track, r_map = cpu_sample_sizes(name)
     sc = CpuScene(wl, n_points, steps + warmup + 2)
     m_pix = wl['map'][1] if wl['map'] else 0
@@ -694,7 +753,7 @@ def run_reference(args):
     points = args.points or wl['points']
     v, threads, dt, desc = cpu_run(args.config, points, args.steps, args.warmup)
     sample = f'per step: {desc}; host cores ({threads} torch threads of {os.cpu_count()}; oracle port of the reference, exact cKDTree kNN)'
-    render_mode = wl['mode'] == 'render'
+    render_mode = wl['mode'] in ('render', 'rerender')
     out = {'impl': 'reference', 'metric': 'ray-samples/sec (render+kNN+MLP' + (' forward' if render_mode else ' fwd+bwd, frame step') + ')',
            'value': v, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dt * 1e3 / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

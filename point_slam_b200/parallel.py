@@ -158,3 +158,30 @@ def render_img_sharded(render_rows, H: int, W: int, device, group=None):
         parts.append(out[r][:b - a])
     full = torch.cat(parts, 0)
     return full[..., 0], full[..., 1], full[..., 2:]
+
+
+def rerender_frames(renderer, npc, decoders, frames, device, every_frame=1, group=None):
+    """Frame-parallel end-of-run re-render (Mapper.py:826-876: every `every_frame`-th frame of the sequence is rendered from its
+    estimated pose and compared with the sensor images).  frames[k] = dict(c2w (4,4) / (3,4), depth (H,W), color (H,W,3), dyn_r_query
+    (H,W) f64 or None) on the device; rank r of a process group renders frames r, r + world, ... of the selected ones (no
+    collective until the end: one all_reduce of three sums).  -> dict(frames, psnr, depth_l1) averaged over all ranks' frames,
+    with the reference's definitions: PSNR = -10 log10(mse over pixels with depth > 0) (:868-870), depth L1 = mean |d_gt - d| over
+    the same pixels (:884-885).  (MS-SSIM / LPIPS need pytorch_msssim / torchmetrics, which this image lacks.)"""
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    sel = list(range(0, len(frames), every_frame))
+    acc = torch.zeros(3, dtype=torch.float64, device=device)
+    outs = {}
+    for k in shard_strided(len(sel), rank, world):
+        f = frames[sel[k]]
+        d, _, c = renderer.render_img(npc, decoders, f['c2w'], device, 'color', gt_depth=f['depth'], npc_geo_feats=npc.get_geo_feats(),
+                                      npc_col_feats=npc.get_col_feats(), dynamic_r_query=f.get('dyn_r_query'),
+                                      cloud_pos=npc.cloud_pos_tensor())
+        m = f['depth'] > 0
+        mse = torch.nn.functional.mse_loss(f['color'][m], c[m])
+        acc += torch.stack([-10.0 * torch.log10(mse).double(), torch.abs(f['depth'][m] - d[m].float()).mean().double(),
+                            torch.ones((), dtype=torch.float64, device=device)])
+        outs[sel[k]] = (d, c)
+    if world > 1:
+        dist.all_reduce(acc, group=group)
+    n = max(float(acc[2]), 1.0)
+    return dict(frames=int(acc[2]), psnr=float(acc[0]) / n, depth_l1=float(acc[1]) / n, rendered=outs)
