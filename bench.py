@@ -206,6 +206,7 @@ class GpuScene:
         self.map_ev = []
         self.added = 0
         self.channel = None
+        self.delta_ev = []
 
     def _to_device(self, f):
         d = self.device
@@ -239,8 +240,13 @@ class GpuScene:
         from point_slam_b200 import parallel as PAR
         if self.channel is None:
             self.channel = PAR.DeltaChannel(self.device, PAR.n_decoder_floats(self.decoders))
-        delta = PAR.make_delta(self.npc, self.decoders, n0, rows) if self.rank == 0 else None
-        PAR.apply_delta(self.npc, self.decoders, self.channel.broadcast(delta, 0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if self.rank == 0:
+            self.channel.pack_from(self.npc, self.decoders, n0, rows)
+        PAR.apply_delta(self.npc, self.decoders, self.channel.broadcast(None, 0))
+        e1.record()
+        self.delta_ev.append((e0, e1))
 
     def step(self, k, from_host, graphs=True):
         """Process frame k.  graphs=True: each iteration is one CUDA-graph replay of the static-shape shell
@@ -541,7 +547,9 @@ def run_ours(args):
         'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
                    'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms,
-                   'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0)},
+                   'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0),
+                   'map_delta_ms_per_step': (float(np.mean([a.elapsed_time(b) for a, b in scene.delta_ev[-2 * args.steps:]]))
+                                             if getattr(scene, 'delta_ev', None) else None)},
         'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': scene.h2d_bytes,
                 'd2h_bytes_per_step': 32 if not render_mode else scene.out_host.numel() * scene.out_host.element_size(),
                 'ms_per_step': ms_e2e / args.steps},

@@ -243,6 +243,8 @@ int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_samples, int32
  * ------------------------------------------------------------------------- */
 size_t psl_tc_blob_floats(void);
 int psl_tc_pack_params(const psl_decoder_params* params_host, float* tc_blob, psl_stream_t stream);
+/* only the folded fp32 rows + small vectors of the above (what psl_h2_pack_params / psl_h2_bwd_pack_params read), no tf32 images */
+int psl_tc_fold_params(const psl_decoder_params* params_host, float* tc_blob, psl_stream_t stream);
 int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
                      const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos,
                      const float* col_feats, const float* rand_col, const float* exposure_affine, float* raw,
@@ -258,6 +260,16 @@ int psl_h2_pack_params(const psl_decoder_params* params_host, const float* tc_bl
 int psl_color_fwd_h2(const psl_decode_cfg* cfg, const void* h2_blob, const float* pos, int64_t m, const int32_t* I,
                      const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
                      const float* rand_col, const float* exposure_affine, float* raw, float* tsave, psl_stream_t stream);
+
+/* Round-2 backward (data gradients) of the colour branch on f16 hi/lo planes with a per-row power-of-two gradient scale
+ * (csrc/psl_color_bwd_h2.cu): contract of psl_color_bwd_tc, operand image from psl_h2_bwd_pack_params (psl_h2_bwd_blob_bytes()). */
+size_t psl_h2_bwd_blob_bytes(void);
+int psl_h2_bwd_pack_params(const psl_decoder_params* params_host, const float* tc_blob, void* h2_bwd_blob, psl_stream_t stream);
+int psl_color_bwd_h2(const psl_decode_cfg* cfg, const void* h2_bwd_blob, const float* pos, int64_t m, const int32_t* I,
+                     const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
+                     const float* exposure_affine, const float* raw, const float* d_raw, const float* tsave, float* tbwd,
+                     float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
+                     psl_stream_t stream);
 
 /* EXPERIMENT, same contract as psl_color_fwd_tc: 16 worker warps (4 threads per sample row, 16-column epilogue chunks) instead
  * of 8 -- csrc/psl_color_tc_w16.cu.  Not on the default path (PSL_W16=1 selects it in ops.py); written after the last GPU

@@ -20,7 +20,7 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------------------------
 // weight folding + packing
 // ---------------------------------------------------------------------------------------------------------------------
-struct FoldArgs { psl_decoder_params P; float* fold; float* blob; };
+struct FoldArgs { psl_decoder_params P; float* fold; float* blob; int job0; };
 
 // grid (6, 128), block 64: row n of layer l:  [e part | act part | (L_act Fc_{l-1}) ] and the folded bias
 __global__ void k_tc_fold(FoldArgs a) {
@@ -59,7 +59,7 @@ __global__ void k_tc_fold(FoldArgs a) {
 
 // split into tf32 hi/lo planes and lay out the canonical chunk images
 __global__ void k_tc_pack(FoldArgs a) {
-    const int job = blockIdx.y;
+    const int job = blockIdx.y + a.job0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (job < NLAYER) {
         const int l = job, N = l_n(l), Kf = l_ks(l) * 8;
@@ -466,10 +466,24 @@ extern "C" int psl_tc_pack_params(const psl_decoder_params* P, float* blob, psl_
     cudaStream_t st = as_stream(stream);
     PSL_CHECK_CUDA(cudaMemsetAsync(blob, 0, sizeof(float) * ctc::TB_TOTAL, st));
     ctc::FoldArgs fa;
-    fa.P = *P; fa.blob = blob; fa.fold = blob + ctc::TB_TOTAL;
+    fa.P = *P; fa.blob = blob; fa.fold = blob + ctc::TB_TOTAL; fa.job0 = 0;
     TimingScope ts(T_PACK, st, 3);
     ctc::k_tc_fold<<<dim3(ctc::NLAYER, 128), 64, 0, st>>>(fa);
     ctc::k_tc_pack<<<dim3((128 * 200 + 255) / 256, ctc::NLAYER + 3), 256, 0, st>>>(fa);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// the part of psl_tc_pack_params the f16-plane kernels need: folded fp32 rows (behind the blob) and the small-vector section
+// (biases, Fourier bases); the tf32 chunk images are NOT written
+extern "C" int psl_tc_fold_params(const psl_decoder_params* P, float* blob, psl_stream_t stream) {
+    PSL_REQUIRE(P && blob, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    ctc::FoldArgs fa;
+    fa.P = *P; fa.blob = blob; fa.fold = blob + ctc::TB_TOTAL; fa.job0 = ctc::NLAYER + 2;
+    TimingScope ts(T_PACK, st, 2);
+    ctc::k_tc_fold<<<dim3(ctc::NLAYER, 128), 64, 0, st>>>(fa);
+    ctc::k_tc_pack<<<dim3(1, 1), 256, 0, st>>>(fa);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -238,6 +238,7 @@ USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-b
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
 USE_W16_FORWARD = os.environ.get('PSL_W16', '1') == '1'       # 16-worker-warp colour forward (psl_color_tc_w16.cu); bit-identical to the 8-warp kernel, 11 % faster (profiles/r02_s1)
 USE_W16_BACKWARD = os.environ.get('PSL_W16', '1') == '1'      # 16-worker-warp colour backward (psl_color_bwd_tc_w16.cu); bit-identical, 14 % faster
+USE_H2_BACKWARD = os.environ.get('PSL_H2_BWD', '1') != '0'     # f16-plane colour backward with per-row gradient scaling (psl_color_bwd_h2.cu)
 USE_H2_FORWARD = os.environ.get('PSL_H2', '1') != '0'           # f16-plane, two-tiles-in-flight colour forward (psl_color_h2.cu)
 OVERLAP_BRANCHES = os.environ.get('PSL_OVERLAP', '1') != '0'  # geometry kernel on a forked stream next to the colour kernel
 _SIDE = {}
@@ -261,17 +262,31 @@ class PackedDecoder:
         self.blob = torch.empty(lib.psl_tc_blob_floats(), dtype=torch.float32, device=device)
         self.bblob = torch.empty(lib.psl_tc_bwd_blob_floats(), dtype=torch.float32, device=device)
         self.hblob = torch.empty(lib.psl_h2_blob_bytes(), dtype=torch.uint8, device=device)      # f16 hi/lo planes (psl_color_h2.cu)
+        self.bhblob = torch.empty(lib.psl_h2_bwd_blob_bytes(), dtype=torch.uint8, device=device)  # ... of the backward (psl_color_bwd_h2.cu)
 
     def pack(self, params, backward=True):
         lib = L.load()
         pstruct = _param_struct([_f32c(p.detach()) for p in params])
         L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(self.packed), L.stream()), 'psl_pack_params')
-        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(self.blob), L.stream()), 'psl_tc_pack_params')
-        L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(self.blob), L.ptr(self.hblob), L.stream()), 'psl_h2_pack_params')
+        _tc_fold_or_pack(lib, pstruct, self.blob)
+        if USE_H2_FORWARD:
+            L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(self.blob), L.ptr(self.hblob), L.stream()), 'psl_h2_pack_params')
         if backward:
-            L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(self.blob), lib.psl_tc_fold_offset_floats(), L.ptr(self.bblob),
-                                               L.stream()), 'psl_tc_bwd_pack_params')
+            if USE_H2_BACKWARD:
+                L.check(lib.psl_h2_bwd_pack_params(C.byref(pstruct), L.ptr(self.blob), L.ptr(self.bhblob), L.stream()), 'psl_h2_bwd_pack_params')
+            else:
+                L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(self.blob), lib.psl_tc_fold_offset_floats(), L.ptr(self.bblob),
+                                                   L.stream()), 'psl_tc_bwd_pack_params')
         return self
+
+
+def _tc_fold_or_pack(lib, pstruct, blob):
+    """Folded fp32 rows + small vectors (all the f16-plane kernels read), plus the tf32 chunk images only when a 3xTF32 kernel is
+    still selected (PSL_H2=0 / PSL_H2_BWD=0 A/B runs)."""
+    if USE_H2_FORWARD and USE_H2_BACKWARD and USE_TC_BACKWARD and USE_TC_WGRAD and USE_TENSOR_CORES:
+        L.check(lib.psl_tc_fold_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_fold_params')
+    else:
+        L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
 
 
 _DEFAULT_PACK = {}
@@ -317,7 +332,7 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         blob = pk.blob
         use_h2 = USE_H2_FORWARD and (tc_bwd or not need_grad)
         if not prepacked:
-            L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+            _tc_fold_or_pack(lib, pstruct, blob)
             if use_h2:
                 L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(blob), L.ptr(pk.hblob), L.stream()), 'psl_h2_pack_params')
         main = torch.cuda.current_stream(dev)
@@ -389,10 +404,13 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         # colour branch on tensor cores (data gradients), then geometry branch + IDW weights + d_pos on the FFMA kernel
         blob, bblob = pk.blob, pk.bblob
         if repack is True:
-            L.check(lib.psl_tc_pack_params(C.byref(pstruct), L.ptr(blob), L.stream()), 'psl_tc_pack_params')
+            _tc_fold_or_pack(lib, pstruct, blob)
         if repack:
-            L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(blob), lib.psl_tc_fold_offset_floats(), L.ptr(bblob), L.stream()),
-                    'psl_tc_bwd_pack_params')
+            if USE_H2_BACKWARD:
+                L.check(lib.psl_h2_bwd_pack_params(C.byref(pstruct), L.ptr(blob), L.ptr(pk.bhblob), L.stream()), 'psl_h2_bwd_pack_params')
+            else:
+                L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(blob), lib.psl_tc_fold_offset_floats(), L.ptr(bblob), L.stream()),
+                        'psl_tc_bwd_pack_params')
         tbwd = torch.empty(lib.psl_tc_bwd_tmp_floats(M, cfg.encode_rel_pos), dtype=torch.float32, device=dev)
         if wn is None:
             wn = torch.empty((M, 8), dtype=torch.float32, device=dev)
@@ -417,8 +435,8 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
         if side is not None:
             side.wait_stream(main)
-        bwd_tc = lib.psl_color_bwd_tc_w16 if USE_W16_BACKWARD else lib.psl_color_bwd_tc
-        L.check(bwd_tc(C.byref(cfg), L.ptr(bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+        bwd_tc = lib.psl_color_bwd_h2 if USE_H2_BACKWARD else (lib.psl_color_bwd_tc_w16 if USE_W16_BACKWARD else lib.psl_color_bwd_tc)
+        L.check(bwd_tc(C.byref(cfg), L.ptr(pk.bhblob if USE_H2_BACKWARD else bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                        L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
                        L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
                        int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')

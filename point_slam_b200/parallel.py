@@ -90,6 +90,8 @@ class DeltaChannel:
         self.o_upd = self.o_new + 67 * self.k_max
         self.o_dec = self.o_upd + 64 * self.u_max
         self.buf = torch.zeros(self.o_dec + self.n_dec, dtype=torch.float32, device=device)
+        self._rows = torch.empty(self.u_max, 32, dtype=torch.float32, device=device)     # gather scratch (no allocator traffic per delta)
+        self._hdr_host = torch.zeros(4, dtype=torch.int32).pin_memory() if torch.cuda.is_available() and str(device) != 'cpu' else torch.zeros(4, dtype=torch.int32)
 
     def pack(self, d: MapDelta):
         K, U = d.pos_new.shape[0], d.upd_idx.shape[0]
@@ -103,6 +105,29 @@ class DeltaChannel:
             b[self.o_new:self.o_new + 67 * K].view(K, 67).copy_(torch.cat([d.pos_new, d.geo_new, d.col_new], 1))
         b[self.o_dec:].copy_(d.decoder_flat)
 
+    def pack_from(self, npc, decoders, n_before: int, upd_idx: Optional[torch.Tensor]):
+        """make_delta + pack without temporaries: the changed rows are gathered straight into the channel buffer."""
+        pos, geo, col = npc.cloud_pos_tensor(), npc.get_geo_feats(), npc.get_col_feats()
+        K = pos.shape[0] - int(n_before)
+        U = 0 if upd_idx is None else int(upd_idx.shape[0])
+        assert 0 <= K <= self.k_max and U <= self.u_max, 'map delta exceeds the channel capacity'
+        b = self.buf
+        self._hdr_host[0], self._hdr_host[1], self._hdr_host[2] = int(n_before), K, U
+        b[:self.HDR].view(torch.int32).copy_(self._hdr_host, non_blocking=True)
+        if K:
+            new = b[self.o_new:self.o_new + 67 * K].view(K, 67)
+            new[:, :3].copy_(pos[n_before:]); new[:, 3:35].copy_(geo[n_before:]); new[:, 35:].copy_(col[n_before:])
+        if U:
+            idx = upd_idx.to(b.device).long()
+            b[self.o_idx:self.o_idx + 2 * U].view(torch.int64).copy_(idx)
+            upd = b[self.o_upd:self.o_upd + 64 * U].view(U, 64)
+            torch.index_select(geo, 0, idx, out=self._rows[:U]); upd[:, :32].copy_(self._rows[:U])
+            torch.index_select(col, 0, idx, out=self._rows[:U]); upd[:, 32:].copy_(self._rows[:U])
+        off = self.o_dec
+        for p in decoders.color_decoder.parameters():
+            b[off:off + p.numel()].copy_(p.detach().reshape(-1))
+            off += p.numel()
+
     def unpack(self) -> MapDelta:
         b = self.buf
         n_before, K, U, _ = (int(v) for v in b[:self.HDR].view(torch.int32).tolist())     # the receiver's one host read
@@ -112,8 +137,8 @@ class DeltaChannel:
         return MapDelta(n_before, new[:, :3], new[:, 3:35], new[:, 35:], idx, upd[:, :32], upd[:, 32:], b[self.o_dec:])
 
     def broadcast(self, delta: Optional[MapDelta], src: int, group=None) -> MapDelta:
-        """All ranks call this; `delta` is read on `src`.  One dist.broadcast."""
-        if dist.get_rank(group) == src:
+        """All ranks call this; `delta` is read on `src` (None: the source already filled the buffer with pack_from).  One dist.broadcast."""
+        if dist.get_rank(group) == src and delta is not None:
             self.pack(delta)
         dist.broadcast(self.buf, src, group=group)
         return self.unpack()

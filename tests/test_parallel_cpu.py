@@ -89,8 +89,8 @@ def _worker(rank, world, port, ret):
             with torch.no_grad():
                 for p in dec.color_decoder.parameters():
                     p.mul_(1.01)
-            delta = PL.make_delta(npc, dec, n0, idx)
-        PL.apply_delta(npc, dec, ch.broadcast(delta, 0))
+            ch.pack_from(npc, dec, n0, idx)                # gathers straight into the channel buffer
+        PL.apply_delta(npc, dec, ch.broadcast(None, 0))
         flat = torch.cat([npc.cloud_pos_tensor().reshape(-1), npc.get_geo_feats().reshape(-1), npc.get_col_feats().reshape(-1),
                           torch.cat([p.detach().reshape(-1) for p in dec.color_decoder.parameters()])]).double()
         sig = torch.stack([flat.sum(), (flat * torch.arange(flat.numel(), dtype=torch.float64)).sum(), torch.tensor(float(npc.pts_num()))])
