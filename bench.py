@@ -204,6 +204,7 @@ class GpuScene:
                                       lr=tc['lr'], w_color=tc['w_color_loss'], separate_lr=tc['separate_LR'])
         self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, wl['map'][1], device) if wl['map'] else None
         self.map_ev = []
+        self.map_host = []                # host wall time of the same section (it holds the step's host syncs)
         self.added = 0
         self.channel = None
         self.delta_ev = []
@@ -271,6 +272,7 @@ class GpuScene:
             m_it, m_rays = wl['map']
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            h0 = time.perf_counter()
             c2w = torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True)
             n0 = self.map_update(c2w, tr.depth, tr.color)
             cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=c2w)
@@ -280,6 +282,7 @@ class GpuScene:
             self.mapper.begin_frame(idx, [cur] + self.keyframes)
             e1.record()
             self.map_ev.append((e0, e1))
+            self.map_host.append((time.perf_counter() - h0) * 1e3)
             g = geo_iters(m_it)
             if graphs:
                 self.mapper.run('geometry', g)
@@ -457,7 +460,9 @@ def run_ours(args):
     recaptures = scene.captures() - cap0
     map_ms = None
     if getattr(scene, 'map_ev', None):
-        map_ms = float(np.mean([a.elapsed_time(b) for a, b in scene.map_ev[-2 * args.steps:]]))
+        map_each = [round(a.elapsed_time(b), 2) for a, b in scene.map_ev[-2 * args.steps:]]
+        map_ms = float(np.median(map_each))
+        map_host_each = [round(v, 2) for v in scene.map_host[-2 * args.steps:]]
     # per-kernel device time of one more step (CUDA events on the launching stream inside the library): the same static-shape
     # iterations launched eagerly (graph replays bypass the host-side event hooks), geometry kernels in-line (no stream fork:
     # a forked kernel's slot would include the time it waits for free SMs and could be mistaken for the dominant kernel)
@@ -546,7 +551,8 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
         'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
-                   'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms,
+                   'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
+                   'map_update_host_ms_each': map_host_each if map_ms is not None else None,
                    'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0),
                    'map_delta_ms_per_step': (float(np.mean([a.elapsed_time(b) for a, b in scene.delta_ev[-2 * args.steps:]]))
                                              if getattr(scene, 'delta_ev', None) else None)},

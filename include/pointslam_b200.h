@@ -87,6 +87,12 @@ size_t psl_grid_sort_ws_bytes(int64_t n);
  * of occupied cells through *n_cells_host (synchronises `stream`). */
 int psl_grid_sort(const float* cloud_pos, int64_t n, float cell, float* sorted_pts, uint64_t* sorted_keys,
                   void* ws, size_t ws_bytes, int64_t* n_cells_host, psl_stream_t stream);
+/* step 1, incremental: after an append only the k_new new points (cloud_pos[n_old : n_old + k_new]) are keyed and sorted, then merged
+ * (stable) into sorted_pts / sorted_keys IN PLACE (room for n_old + k_new entries) -- bit-identical to psl_grid_sort on the whole
+ * cloud, without its 8 radix passes over every point.  This is the faiss `index.add(pts)` of neural_point.py:164. */
+size_t psl_grid_append_ws_bytes(int64_t n_total, int64_t k_new);
+int psl_grid_append(const float* cloud_pos, int64_t n_old, int64_t k_new, float cell, float* sorted_pts, uint64_t* sorted_keys,
+                    void* ws, size_t ws_bytes, int64_t* n_cells_host, psl_stream_t stream);
 /* step 2: fill the open-addressing table (capacity = power of two >= 2*n_cells, caller-allocated). */
 int psl_grid_hash(const uint64_t* sorted_keys, int64_t n, uint64_t* table_keys, uint32_t* table_vals,
                   uint32_t capacity, psl_stream_t stream);
@@ -236,7 +242,8 @@ int psl_ray_mask(const uint8_t* has_nb, int64_t n_rays, int32_t n_samples, int32
                  psl_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
- * tensor-core (tcgen05, 3xTF32, TMEM-resident activations) colour branch, inference forward.
+ * tensor-core (tcgen05, 3xTF32, TMEM-resident activations, 16 worker warps) colour branch: the A/B baseline of the f16-plane
+ * kernels below (PSL_H2=0 / PSL_H2_BWD=0) and the producer of FFMA-layout activations.
  * psl_tc_pack_params folds fc_c into the next layer and lays the weights out as canonical K-major tf32 hi/lo chunk
  * images (blob: psl_tc_blob_floats() floats).  psl_color_fwd_tc writes raw[:, 0:3]; raw[:, 3] and has_nb come from
  * psl_decode_fwd(stage = PSL_STAGE_GEOMETRY) on the same kNN result.  Same reference lines as psl_decode_fwd.
@@ -271,14 +278,6 @@ int psl_color_bwd_h2(const psl_decode_cfg* cfg, const void* h2_bwd_blob, const f
                      float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
                      psl_stream_t stream);
 
-/* EXPERIMENT, same contract as psl_color_fwd_tc: 16 worker warps (4 threads per sample row, 16-column epilogue chunks) instead
- * of 8 -- csrc/psl_color_tc_w16.cu.  Not on the default path (PSL_W16=1 selects it in ops.py); written after the last GPU
- * session of round 1 and not yet run on hardware. */
-int psl_color_fwd_tc_w16(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m, const int32_t* I,
-                         const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
-                         const float* rand_col, const float* exposure_affine, float* raw, float* save, float* tsave,
-                         psl_stream_t stream);
-
 /* tensor-core training path of the colour branch: psl_color_fwd_tc(tsave) -> psl_color_bwd_tc (data gradients; the
  * geometry branch, the IDW-weight gradient and d_pos are finished by psl_decode_bwd(stage = GEOMETRY, dwn_extra, dpos_extra)). */
 size_t psl_tc_fold_offset_floats(void);
@@ -293,13 +292,6 @@ int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob, const flo
                      float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
                      psl_stream_t stream);
 
-/* EXPERIMENT, same contract as psl_color_bwd_tc: 16 worker warps, the half-0-only steps of the production kernel spread over
- * four column quarters -- csrc/psl_color_bwd_tc_w16.cu.  Not on the default path (PSL_W16=1), not yet run on hardware. */
-int psl_color_bwd_tc_w16(const psl_decode_cfg* cfg, const float* bwd_blob, const float* pos, int64_t m, const int32_t* I,
-                         const float* D, const int32_t* nnum, const double* r2, const float* cloud_pos, const float* col_feats,
-                         const float* exposure_affine, const float* raw, const float* d_raw, const float* tsave, float* tbwd,
-                         float* d_colpair, float* wn_out, float* dwn_col, float* dpos_col, int32_t want_wgrad, int32_t* grid_out,
-                         psl_stream_t stream);
 
 /* weight gradients of the colour branch (GEMMs over the sample index) from the buffers left by psl_color_fwd_tc(tsave) and
  * psl_color_bwd_tc(want_wgrad = 1); only the c_* entries of `grads_host` are written.  ws: psl_wgrad_tc_ws_floats(m). */
@@ -373,12 +365,6 @@ size_t psl_frustum_select_ws_bytes(int64_t n);
 int psl_frustum_select(const float* cloud_pos, int64_t n, const double* w2c_host, double fx, double fy, double cx, double cy,
                        const float* depth, int32_t H, int32_t W, int32_t edge, uint8_t* mask, int64_t* indices,
                        int32_t* count, void* ws, size_t ws_bytes, psl_stream_t stream);
-
-/* self-test of the tcgen05 building blocks: D (128,N) = A (128,K) W (N,K)^T with 3xTF32; mode 0: A in TMEM, 1: A in smem */
-int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
-/* same self-test with 16-bit operand planes (kind::f16: hi = f16, lo = bf16, formats mixed per MMA): mode 2 = TS (A in TMEM, two k per
-   column), mode 3 = SS; scratch N*K floats */
-int psl_tc_gemm_test_h(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, int variant, psl_stream_t stream);
 
 #ifdef __cplusplus
 }

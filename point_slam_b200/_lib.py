@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 # PSL_LIB: load another build of the same sources (A/B experiments, e.g. one compiled with -DPSL_PRECISE_TRIG)
 LIB_PATH = os.environ.get('PSL_LIB') or os.path.join(_HERE, 'libpointslam_b200.so')
-SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_tc_test.cu', 'psl_color_tc.cu', 'psl_color_tc_w16.cu', 'psl_color_h2.cu', 'psl_color_bwd_h2.cu', 'psl_color_bwd_tc.cu', 'psl_color_bwd_tc_w16.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu', 'psl_map.cu']
+SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_composite.cu', 'psl_color_tc.cu', 'psl_color_tc_w16.cu', 'psl_color_h2.cu', 'psl_color_bwd_h2.cu', 'psl_color_bwd_tc.cu', 'psl_color_bwd_tc_w16.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu', 'psl_map.cu']
 HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_grid.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh', 'psl_color_tc.cuh', 'psl_color_bwd_tc.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
@@ -57,6 +57,8 @@ _SIGS = {
     'psl_timing_collect': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     'psl_grid_sort_ws_bytes': (_sz, [_i64]),
     'psl_grid_sort': (C.c_int, [_vp, _i64, _f32, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
+    'psl_grid_append_ws_bytes': (_sz, [_i64, _i64]),
+    'psl_grid_append': (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
     'psl_grid_hash': (C.c_int, [_vp, _i64, _vp, _vp, C.c_uint32, _vp]),
     'psl_knn_query': (C.c_int, [C.POINTER(Grid), _vp, _i64, _vp, _f64, _i32, _vp, _vp, _vp, _vp]),
     'psl_raymarch_knn': (C.c_int, [C.POINTER(Grid), _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _vp, _vp, _f64,
@@ -97,7 +99,6 @@ _SIGS = {
     'psl_h2_bwd_pack_params': (C.c_int, [C.POINTER(DecoderParams), _vp, _vp, _vp]),
     'psl_color_bwd_h2': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp]),
-    'psl_color_fwd_tc_w16': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_wgrad_tc_ws_floats': (_sz, [_i64]),
     'psl_wgrad_tc': (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(DecoderParams), _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32,
                                C.POINTER(DecoderParams), _vp, _vp, _sz, _vp]),
@@ -114,14 +115,45 @@ _SIGS = {
     'psl_frustum_select_ws_bytes': (_sz, [_i64]),
     'psl_frustum_select': (C.c_int, [_vp, _i64, C.POINTER(_f64), _f64, _f64, _f64, _f64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                      _sz, _vp]),
-    'psl_color_bwd_tc_w16': (C.c_int, [C.POINTER(DecodeCfg), _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp]),
-    'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-    'psl_tc_gemm_test_h': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)
 
 _lib = None
+
+
+# the tcgen05 building-block self-test (csrc/psl_tc_test.cu) is test infrastructure: its own small library, not in the product .so
+TEST_LIB_PATH = os.path.join(_HERE, 'libpsl_tctest.so')
+TEST_SOURCES = ['psl_tc_test.cu', 'psl_api.cu']
+_TEST_SIGS = {
+    'psl_tc_gemm_test': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'psl_tc_gemm_test_h': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+}
+_test_lib = None
+
+
+def build_test_lib(force: bool = False) -> str:
+    deps = [os.path.join(_HERE, 'csrc', f) for f in TEST_SOURCES + ['psl_tc.cuh', 'psl_common.cuh']]
+    if not force and os.path.exists(TEST_LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(TEST_LIB_PATH) for d in deps):
+        return TEST_LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-o', TEST_LIB_PATH] + [os.path.join(_HERE, 'csrc', f) for f in TEST_SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    return TEST_LIB_PATH
+
+
+def load_test_lib():
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise RuntimeError(f'{TEST_LIB_PATH} is missing: __graft_entry__.build() compiles it')
+        lib = C.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in _TEST_SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _test_lib = lib
+    return _test_lib
 
 
 def needs_build() -> bool:

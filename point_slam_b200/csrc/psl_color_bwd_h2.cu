@@ -585,13 +585,8 @@ extern "C" int psl_color_bwd_h2(const psl_decode_cfg* cfg, const void* h2_bwd_bl
     a.part_brel = tbwd + tbwd_layout(m, cfg->encode_rel_pos).total;
     a.want_wgrad = want_wgrad;
     const long long n_tiles = (m + cbt::TM - 1) / cbt::TM;
-    int dev = 0;
-    PSL_CHECK_CUDA(cudaGetDevice(&dev));
-    static bool attr_set[64] = {};
-    if (dev < 64 && !attr_set[dev]) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(cbh::k_color_bwd_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, cbh::S_TOTAL));
-        attr_set[dev] = true;
-    }
+    // per launch: the attribute belongs to the device the launch goes to
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(cbh::k_color_bwd_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, cbh::S_TOTAL));
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (grid_out) *grid_out = (int32_t)grid;
     TimingScope ts(T_COLOR_BWD_TC, as_stream(stream));

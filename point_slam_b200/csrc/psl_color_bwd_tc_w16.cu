@@ -1,5 +1,5 @@
-// EXPERIMENT (not on the default path; selected with PSL_W16=1 in point_slam_b200/ops.py): the tensor-core colour backward of
-// psl_color_bwd_tc.cu with SIXTEEN worker warps -- four threads per sample row.  Thread (row r, quarter q) owns columns
+// 3xTF32 colour backward, data gradients (the A/B baseline of psl_color_bwd_h2.cu, selected with PSL_H2_BWD=0): the round-1
+// kernel with SIXTEEN worker warps -- four threads per sample row.  Thread (row r, quarter q) owns columns
 // 32q..32q+31 of every 128-wide gradient plane (two 16-column chunks), and the steps the production kernel runs on its half-0
 // warps only are spread over the quarters:
 //   q0  dL/d(output) operand, colour-embedding -> d_pos, rel-pos backward of every neighbour (d_pos, dBrel), d_pos store
@@ -9,15 +9,14 @@
 // Every output element is produced by the same arithmetic in the same order as in the production kernel, so results must be
 // bit-identical.  Same operand blob, TMEM regions, shared-memory map, producer and MMA issue order (psl_color_bwd_tc.cuh).
 //
-// Status: written after the last GPU session of round 1 -- compiles for sm_100a, NOT yet run on hardware; watchdog traps on every
-// mbarrier wait.  tests/test_gpu_tc.py::test_w16_experiment runs it only when PSL_EXPERIMENTAL=1.
+// Verified bit-identical to the round-1 8-worker-warp kernel on hardware (profiles/r02_s1_*) before that kernel was removed.
 #include "psl_color_bwd_tc.cuh"
 
 namespace psl {
 namespace cbt16 {
 
 using namespace cbt;
-using tc::mbar_wait_wd;
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) { tc::mbar_wait_p(bar, parity); }
 
 constexpr int NWORK16 = 512, NTHR16 = 576;      // warps 0-15 workers, 16 bulk-copy producer, 17 TMEM allocator + MMA issuer
 
@@ -446,7 +445,7 @@ __global__ void __launch_bounds__(NTHR16, 1) k_color_bwd_tc_w16(Args a, long lon
 using namespace psl;
 
 // same contract as psl_color_bwd_tc (include/pointslam_b200.h); experiment build of the worker side, see the file header
-extern "C" int psl_color_bwd_tc_w16(const psl_decode_cfg* cfg, const float* bwd_blob, const float* pos, int64_t m,
+extern "C" int psl_color_bwd_tc(const psl_decode_cfg* cfg, const float* bwd_blob, const float* pos, int64_t m,
                                     const int32_t* I, const float* D, const int32_t* nnum, const double* r2,
                                     const float* cloud_pos, const float* col_feats, const float* exposure_affine,
                                     const float* raw, const float* d_raw, const float* tsave, float* tbwd, float* d_colpair,
@@ -462,11 +461,7 @@ extern "C" int psl_color_bwd_tc_w16(const psl_decode_cfg* cfg, const float* bwd_
     a.part_brel = tbwd + tbwd_layout(m, cfg->encode_rel_pos).total;
     a.want_wgrad = want_wgrad;
     const long long n_tiles = (m + cbt::TM - 1) / cbt::TM;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(cbt16::k_color_bwd_tc_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, cbt::SB_TOTAL));
-        attr_set = true;
-    }
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(cbt16::k_color_bwd_tc_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, cbt::SB_TOTAL));
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (grid_out) *grid_out = (int32_t)grid;
     TimingScope ts(T_COLOR_BWD_TC, as_stream(stream));

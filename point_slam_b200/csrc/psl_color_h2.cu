@@ -595,14 +595,9 @@ extern "C" int psl_color_fwd_h2(const psl_decode_cfg* cfg, const void* h2_blob, 
     a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.tsave = tsave;
     const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
     const long long n_pairs = (n_tiles + 1) / 2;
-    int dev = 0;
-    PSL_CHECK_CUDA(cudaGetDevice(&dev));
-    static bool attr_set[64] = {};
-    if (dev < 64 && !attr_set[dev]) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
-        attr_set[dev] = true;
-    }
+    // per launch: the attribute belongs to the device the launch goes to
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
     const long long grid = n_pairs < sm_count() ? n_pairs : sm_count();
     TimingScope ts(T_COLOR_FWD_TC, as_stream(stream));
     const unsigned char* hb = static_cast<const unsigned char*>(h2_blob);

@@ -1,14 +1,12 @@
-// EXPERIMENT (not on the default path; selected with PSL_W16=1 in point_slam_b200/ops.py): the tensor-core colour forward of
-// psl_color_tc.cu with SIXTEEN worker warps -- four threads per sample row, thread (row r, quarter q) owns columns 32q..32q+31
+// 3xTF32 colour forward (the A/B baseline of the f16-plane kernel psl_color_h2.cu, selected with PSL_H2=0, and the producer of the
+// FFMA-layout activations when the tensor-core backward is switched off): SIXTEEN worker warps -- four threads per sample row, thread (row r, quarter q) owns columns 32q..32q+31
 // of every 128-wide layer and walks them as two 16-column chunks (tcgen05.ld.x16 -> bias -> save -> softplus -> hi/lo split ->
 // 2 x tcgen05.st.x16), so that the epilogues fit the 112-register cap of an 18-warp CTA.  Same operand blob, TMEM regions,
 // shared-memory map, bulk-copy producer and MMA issue order as the production kernel (psl_color_tc.cuh); only the worker side
 // and the warp numbering differ.  Motivation and plan: DESIGN.md section 7 item 1, profiles/r01g_summary.md (8 worker warps
 // keep the issue slots 22-27 % busy).
 //
-// Status: written after the last GPU session of round 1 -- compiles for sm_100a, NOT yet run on hardware.  Every mbarrier wait
-// of this kernel carries a clock watchdog (trap after ~2 s) so that a choreography mistake ends the launch with an error
-// instead of hanging the device.  tests/test_gpu_tc.py::test_w16_experiment runs it only when PSL_EXPERIMENTAL=1.
+// Verified bit-identical to the round-1 8-worker-warp kernel on hardware (profiles/r02_s1_*) before that kernel was removed.
 #include "psl_color_tc.cuh"
 
 namespace psl {
@@ -18,7 +16,7 @@ using namespace ctc;
 
 constexpr int NWORK16 = 512, NTHR16 = 576;      // warps 0-15 workers, 16 bulk-copy producer, 17 TMEM allocator + MMA issuer
 
-using tc::mbar_wait_wd;
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) { tc::mbar_wait_p(bar, parity); }
 __device__ __forceinline__ void worker_signal16(uint64_t* a_ready) {
     tc::tmem_st_wait();
     tc::fence_before_sync();
@@ -395,7 +393,7 @@ __global__ void __launch_bounds__(NTHR16, 1) k_color_fwd_tc_w16(Args a, long lon
 using namespace psl;
 
 // same contract as psl_color_fwd_tc (include/pointslam_b200.h); experiment build of the worker side, see the file header
-extern "C" int psl_color_fwd_tc_w16(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m,
+extern "C" int psl_color_fwd_tc(const psl_decode_cfg* cfg, const float* tc_blob, const float* pos, int64_t m,
                                     const int32_t* I, const float* D, const int32_t* nnum, const double* r2,
                                     const float* cloud_pos, const float* col_feats, const float* rand_col,
                                     const float* exposure_affine, float* raw, float* save, float* tsave, psl_stream_t stream) {
@@ -408,13 +406,9 @@ extern "C" int psl_color_fwd_tc_w16(const psl_decode_cfg* cfg, const float* tc_b
     a.cfg = *cfg; a.blob = tc_blob; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
     a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.save = save; a.tsave = tsave;
     const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
-        attr_set = true;
-    }
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(ctc16::k_color_fwd_tc_w16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctc::SB_TOTAL));
     const long long grid = n_tiles < sm_count() ? n_tiles : sm_count();
     TimingScope ts(T_COLOR_FWD_TC, as_stream(stream));
     if (tsave) ctc16::k_color_fwd_tc_w16<2><<<(unsigned)grid, ctc16::NTHR16, ctc::SB_TOTAL, as_stream(stream)>>>(a, n_tiles);

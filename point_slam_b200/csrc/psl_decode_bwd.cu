@@ -987,11 +987,7 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
     a.want_geo_params = wg; a.want_col_params = wc && color;
     const long long n_tiles = (m + TS - 1) / TS;
     const long long grid = bwd_grid(m);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_BYTES));
-        attr_set = true;
-    }
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_BYTES));
     {
         TimingScope ts(T_DECODE_BWD, st, 2);   // memset + kernel
         PSL_CHECK_CUDA(cudaMemsetAsync(a.partial, 0, sizeof(float) * (size_t)GR_TOTAL * grid, st));

@@ -412,12 +412,8 @@ extern "C" int psl_decode_fwd(const psl_decode_cfg* cfg, const float* packed, co
     a.cloud_pos = cloud_pos; a.geo_feats = geo_feats; a.col_feats = col_feats; a.rand_geo = rand_geo;
     a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.has_nb = has_nb; a.save = save;
     const long long n_tiles = (m + TS - 1) / TS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_FWD_BYTES));
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_FWD_BYTES));
-        attr_set = true;
-    }
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_FWD_BYTES));
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_FWD_BYTES));
     long long blocks = n_tiles < sm_count() ? n_tiles : sm_count();
     TimingScope ts(T_DECODE_FWD, as_stream(stream));
     if (save) k_decode_fwd<true><<<(unsigned)blocks, NWARP * 32, SM_FWD_BYTES, as_stream(stream)>>>(a, n_tiles);

@@ -3,6 +3,7 @@
 //
 // Replaces faiss GpuIndexIVFFlat train/add/search as used by src/neural_point.py:37-41,161-164,189-197
 // and the sample placement of src/utils/Renderer.py:133-174.
+#include <cub/device/device_merge.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
 
@@ -33,6 +34,28 @@ __global__ void k_gather_sorted(const float* __restrict__ pos, const uint32_t* _
         out[j] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __uint_as_float(i));
         head = (j == 0) || (keys[j] != keys[j - 1]);
     }
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_cells, (unsigned long long)__popc(b));
+}
+
+// ---- incremental rebuild (append): only the NEW points are keyed and sorted, then merged into the sorted copy ----------------
+__global__ void k_cell_keys_new(const float* __restrict__ pos, int n_old, int k_new, float inv_cell, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k_new) return;
+    const float* p = pos + 3 * (size_t)(n_old + i);
+    keys[i] = cell_key(cell_coord(p[0], inv_cell), cell_coord(p[1], inv_cell), cell_coord(p[2], inv_cell));
+    vals[i] = (uint32_t)(n_old + i);
+}
+__global__ void k_gather_new(const float* __restrict__ pos, const uint32_t* __restrict__ order, int k_new, float4* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k_new) return;
+    const uint32_t i = order[j];
+    out[j] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __uint_as_float(i));
+}
+__global__ void k_count_cells(const uint64_t* __restrict__ keys, int n, unsigned long long* __restrict__ n_cells) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int head = j < n && (j == 0 || keys[j] != keys[j - 1]);
     const unsigned b = __ballot_sync(0xffffffffu, head);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_cells, (unsigned long long)__popc(b));
 }
@@ -336,11 +359,8 @@ static int launch_knn(const GridDev& g, const KnnArgs& a, cudaStream_t st) {
     const long long n_seg = (a.m + a.seg - 1) / a.seg;
     const long long n_work = n_seg * n_chunks;
     const size_t smem = sizeof(float4) * KNN_WARPS * KNN_CAP + sizeof(unsigned long long) * KNN_WARPS * 32 * 8;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[RAYS]) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(k_knn<RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[RAYS] = true;
-    }
+    // per launch: the attribute belongs to the device / context the launch goes to (a process may drive several GPUs)
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(k_knn<RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = (n_work + KNN_WARPS - 1) / KNN_WARPS;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -387,6 +407,66 @@ extern "C" int psl_grid_sort(const float* cloud_pos, int64_t n, float cell, floa
     PSL_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     k_gather_sorted<<<nb, tb, 0, st>>>(cloud_pos, vals_out, sorted_keys, (int)n, reinterpret_cast<float4*>(sorted_pts),
                                        counter);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    PSL_CHECK_CUDA(cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PSL_CHECK_CUDA(cudaStreamSynchronize(st));
+    *n_cells_host = (int64_t)h;
+    return 0;
+}
+
+static size_t append_cub_bytes(int64_t n_total, int64_t k_new, size_t* sort_b, size_t* merge_b) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (int)k_new, 0, 63);
+    cub::DeviceMerge::MergePairs(nullptr, b, (const uint64_t*)nullptr, (const float4*)nullptr, (int)(n_total - k_new), (const uint64_t*)nullptr,
+                                 (const float4*)nullptr, (int)k_new, (uint64_t*)nullptr, (float4*)nullptr);
+    if (sort_b) *sort_b = a;
+    if (merge_b) *merge_b = b;
+    return a > b ? a : b;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t psl_grid_append_ws_bytes(int64_t n_total, int64_t k_new) {
+    return 2 * al256(sizeof(uint64_t) * k_new) + 2 * al256(sizeof(uint32_t) * k_new) + al256(sizeof(float4) * k_new) +
+           al256(sizeof(uint64_t) * n_total) + al256(sizeof(float4) * n_total) + al256(append_cub_bytes(n_total, k_new, nullptr, nullptr)) + 512;
+}
+
+// Rebuild after an append WITHOUT re-sorting the cloud: the first n_old points are already in (sorted_pts, sorted_keys); the k_new
+// appended points (cloud_pos[n_old : n_old + k_new]) are keyed, sorted among themselves and merged in (stable: equal keys keep the old
+// points first, and new indices are larger than old ones -- the result is bit-identical to psl_grid_sort on the whole cloud).
+// sorted_pts / sorted_keys are updated IN PLACE (they must have room for n_old + k_new entries); *n_cells_host as psl_grid_sort.
+extern "C" int psl_grid_append(const float* cloud_pos, int64_t n_old, int64_t k_new, float cell, float* sorted_pts, uint64_t* sorted_keys,
+                               void* ws, size_t ws_bytes, int64_t* n_cells_host, psl_stream_t stream) {
+    PSL_REQUIRE(cloud_pos && sorted_pts && sorted_keys && ws && n_cells_host, "NULL argument");
+    PSL_REQUIRE(n_old > 0 && k_new > 0 && n_old + k_new < (1ll << 31), "append needs an existing sorted cloud and at least one new point");
+    PSL_REQUIRE(cell > 0.f, "cell size must be positive");
+    const int64_t n = n_old + k_new;
+    PSL_REQUIRE(ws_bytes >= psl_grid_append_ws_bytes(n, k_new), "workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    uint64_t* k_in = reinterpret_cast<uint64_t*>(w); w += al256(sizeof(uint64_t) * k_new);
+    uint64_t* k_srt = reinterpret_cast<uint64_t*>(w); w += al256(sizeof(uint64_t) * k_new);
+    uint32_t* v_in = reinterpret_cast<uint32_t*>(w); w += al256(sizeof(uint32_t) * k_new);
+    uint32_t* v_srt = reinterpret_cast<uint32_t*>(w); w += al256(sizeof(uint32_t) * k_new);
+    float4* p_new = reinterpret_cast<float4*>(w); w += al256(sizeof(float4) * k_new);
+    uint64_t* k_out = reinterpret_cast<uint64_t*>(w); w += al256(sizeof(uint64_t) * n);
+    float4* p_out = reinterpret_cast<float4*>(w); w += al256(sizeof(float4) * n);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(w); w += 256;
+    void* cub_tmp = w;
+    size_t sort_b = 0, merge_b = 0;
+    append_cub_bytes(n, k_new, &sort_b, &merge_b);
+    const int tb = 256;
+    TimingScope ts(T_MAP, st, 5);
+    k_cell_keys_new<<<(int)((k_new + tb - 1) / tb), tb, 0, st>>>(cloud_pos, (int)n_old, (int)k_new, 1.0f / cell, k_in, v_in);
+    PSL_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_b, k_in, k_srt, v_in, v_srt, (int)k_new, 0, 63, st));
+    k_gather_new<<<(int)((k_new + tb - 1) / tb), tb, 0, st>>>(cloud_pos, v_srt, (int)k_new, p_new);
+    PSL_CHECK_CUDA(cub::DeviceMerge::MergePairs(cub_tmp, merge_b, (const uint64_t*)sorted_keys, reinterpret_cast<const float4*>(sorted_pts),
+                                                (int)n_old, (const uint64_t*)k_srt, (const float4*)p_new, (int)k_new, k_out, p_out, {}, st));
+    PSL_CHECK_CUDA(cudaMemcpyAsync(sorted_keys, k_out, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+    PSL_CHECK_CUDA(cudaMemcpyAsync(sorted_pts, p_out, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
+    PSL_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    k_count_cells<<<(int)((n + tb - 1) / tb), tb, 0, st>>>(sorted_keys, (int)n, counter);
     PSL_CHECK_CUDA(cudaGetLastError());
     unsigned long long h = 0;
     PSL_CHECK_CUDA(cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(160, 1) k_tc_gemm_test_h(const float* __restri
 }  // namespace psl
 
 using namespace psl;
+extern "C" int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, psl_stream_t stream);
+extern "C" int psl_tc_gemm_test_h(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode, int variant, psl_stream_t stream);
 // A (128,K), W (N,K), D (128,N) device fp32; scratch: 2*N*K floats.  K multiple of 8 (<= 160), N multiple of 16 (<= 128).
 extern "C" int psl_tc_gemm_test(const float* A, const float* W, float* D, float* scratch, int K, int N, int mode,
                                 psl_stream_t stream) {

@@ -602,11 +602,7 @@ extern "C" int psl_wgrad_tc(const psl_decode_cfg* cfg, const psl_decoder_params*
     a.cfg = *cfg; a.P = *P; a.pos = pos; a.m = m; a.I = I; a.cloud_pos = cloud_pos; a.col_feats = col_feats;
     a.tsave = tsave; a.tbwd = tbwd; a.partial = ws;
     const long long n_tiles = (m + 127) / 128, grid = wgrad_grid(m);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSL_CHECK_CUDA(cudaFuncSetAttribute(wgt::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wgt::SB_TOTAL));
-        attr_set = true;
-    }
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(wgt::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wgt::SB_TOTAL));
     float* sums = ws + (size_t)wgt::W_TOTAL * grid;
     {
         TimingScope ts(T_WGRAD_TC, st);

@@ -98,6 +98,8 @@ class SpatialHash:
         self.r_small = 0.0
         self.alloc_gen = 0
         self.build_gen = 0
+        self._covered, self._covered_ptr = 0, 0       # points (and their buffer) the sorted copy currently covers
+        self.incremental_builds = 0
         self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0, None)
 
     def reserve(self, n_points: int, device):
@@ -109,7 +111,8 @@ class SpatialHash:
         self.cap_points = cap
         self.sorted_pts = torch.empty((cap, 4), dtype=torch.float32, device=device)
         self._keys = torch.empty(cap, dtype=torch.int64, device=device)
-        self._ws_bytes = lib.psl_grid_sort_ws_bytes(cap)
+        self._ws_bytes = max(lib.psl_grid_sort_ws_bytes(cap), lib.psl_grid_append_ws_bytes(cap, max(cap // 4, 1)))
+        self._covered = 0                              # the old sorted copy is not carried over
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
         self.table_alloc = 1 << max(4, int(math.ceil(math.log2(2 * cap))))      # worst case: every point in its own cell
         self.table_keys = torch.empty(self.table_alloc, dtype=torch.int64, device=device)
@@ -120,7 +123,9 @@ class SpatialHash:
         self.alloc_gen += 1
         return True
 
-    def build(self, cloud_pos: torch.Tensor):
+    def build(self, cloud_pos: torch.Tensor, appended_from: int = 0):
+        """Cover `cloud_pos`.  `appended_from` = k > 0 is the caller's statement that rows [0, k) are exactly the rows of the previous
+        build (same storage, unchanged): only rows [k, n) are sorted and merged in (psl_grid_append)."""
         lib = L.load()
         pos = _f32c(cloud_pos).reshape(-1, 3)
         n = pos.shape[0]
@@ -129,11 +134,21 @@ class SpatialHash:
         self.build_gen += 1
         if n == 0:
             self.struct = L.Grid(None, None, None, 0, 0, self.cell, 0.0, None)
+            self._covered = 0
             return self
-        self.reserve(n, dev)
+        n_old = self._covered
+        realloc = self.reserve(n, dev)
         n_cells = C.c_int64(0)
-        L.check(lib.psl_grid_sort(L.ptr(pos), n, self.cell, L.ptr(self.sorted_pts), L.ptr(self._keys), L.ptr(self._ws),
-                                  self._ws_bytes, C.byref(n_cells), L.stream()), 'psl_grid_sort')
+        if (INCREMENTAL_HASH and not realloc and 0 < n_old < n and appended_from == n_old and (n - n_old) * 4 <= n and
+                self._covered_ptr == pos.data_ptr() and lib.psl_grid_append_ws_bytes(n, n - n_old) <= self._ws_bytes):
+            # an append to the cloud this hash already covers: sort the new points only and merge (bit-identical to a full sort)
+            L.check(lib.psl_grid_append(L.ptr(pos), n_old, n - n_old, self.cell, L.ptr(self.sorted_pts), L.ptr(self._keys), L.ptr(self._ws),
+                                        self._ws_bytes, C.byref(n_cells), L.stream()), 'psl_grid_append')
+            self.incremental_builds += 1
+        else:
+            L.check(lib.psl_grid_sort(L.ptr(pos), n, self.cell, L.ptr(self.sorted_pts), L.ptr(self._keys), L.ptr(self._ws),
+                                      self._ws_bytes, C.byref(n_cells), L.stream()), 'psl_grid_sort')
+        self._covered, self._covered_ptr = n, pos.data_ptr()
         cap = 1 << max(4, int(math.ceil(math.log2(max(2 * n_cells.value, 2)))))
         assert cap <= self.table_alloc
         self.capacity = cap
@@ -236,8 +251,7 @@ class RenderSettings:
 USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
-USE_W16_FORWARD = os.environ.get('PSL_W16', '1') == '1'       # 16-worker-warp colour forward (psl_color_tc_w16.cu); bit-identical to the 8-warp kernel, 11 % faster (profiles/r02_s1)
-USE_W16_BACKWARD = os.environ.get('PSL_W16', '1') == '1'      # 16-worker-warp colour backward (psl_color_bwd_tc_w16.cu); bit-identical, 14 % faster
+INCREMENTAL_HASH = os.environ.get('PSL_HASH_APPEND', '1') != '0'   # add_neural_points: sort + merge the new points only (psl_grid_append)
 USE_H2_BACKWARD = os.environ.get('PSL_H2_BWD', '1') != '0'     # f16-plane colour backward with per-row gradient scaling (psl_color_bwd_h2.cu)
 USE_H2_FORWARD = os.environ.get('PSL_H2', '1') != '0'           # f16-plane, two-tiles-in-flight colour forward (psl_color_h2.cu)
 OVERLAP_BRANCHES = os.environ.get('PSL_OVERLAP', '1') != '0'  # geometry kernel on a forked stream next to the colour kernel
@@ -344,8 +358,7 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
                                          L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw), L.ptr(tsave),
                                          L.stream()), 'psl_color_fwd_h2')
         else:
-            fwd_tc = lib.psl_color_fwd_tc_w16 if USE_W16_FORWARD else lib.psl_color_fwd_tc
-            L.check(fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
+            L.check(lib.psl_color_fwd_tc(C.byref(cfg), L.ptr(blob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                            L.ptr(cloud_pos), L.ptr(col), L.ptr(rand_col), L.ptr(affine), L.ptr(raw),
                            None if tc_bwd else L.ptr(save), L.ptr(tsave), L.stream()), 'psl_color_fwd_tc')
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
@@ -435,7 +448,7 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
         if side is not None:
             side.wait_stream(main)
-        bwd_tc = lib.psl_color_bwd_h2 if USE_H2_BACKWARD else (lib.psl_color_bwd_tc_w16 if USE_W16_BACKWARD else lib.psl_color_bwd_tc)
+        bwd_tc = lib.psl_color_bwd_h2 if USE_H2_BACKWARD else lib.psl_color_bwd_tc
         L.check(bwd_tc(C.byref(cfg), L.ptr(pk.bhblob if USE_H2_BACKWARD else bblob), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(nn), L.ptr(r2),
                        L.ptr(cloud_pos), L.ptr(col), L.ptr(affine), L.ptr(raw), L.ptr(d_raw), L.ptr(tsave),
                        L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),

@@ -180,9 +180,10 @@ class NeuralPointCloud(object):
             self._pos = self._pos_buf[:self._indexed + k]
             self._pos_list_cache = None
         grew = self._pos.shape[0] != self._indexed
+        before = self._indexed                           # rows the previous build covered (0 after `_cloud_pos = ...`)
         self._indexed = self._pos.shape[0]
         if grew or self._grid.build_gen == 0:            # nothing appended: the hash already covers the cloud
-            self._grid.build(self._pos)
+            self._grid.build(self._pos, appended_from=before)
         self.index.is_trained = True
 
     def _search_all(self, q):

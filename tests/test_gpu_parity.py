@@ -100,6 +100,39 @@ def test_knn_bit_exact_large_cloud():
     assert torch.equal(n.cpu(), no)
 
 
+def test_incremental_hash_append_is_bit_identical_to_full_rebuild():
+    """psl_grid_append (sort the new points + stable merge) == psl_grid_sort on the whole cloud: same sorted copy, same keys, same
+    neighbours; several appends in a row, including points that fall into already occupied cells (duplicates of old positions)."""
+    from point_slam_b200 import ops, synth
+    cloud = torch.from_numpy(synth.make_cloud(120000, seed=9)).to(DEV)
+    extra = cloud[torch.randperm(120000, device=DEV)[:3000]] + 1e-3            # same cells as existing points, mostly
+    buf = torch.empty((200000, 3), device=DEV)
+    buf[:120000] = cloud
+    inc = ops.SpatialHash(0.08)
+    inc.reserve(200000, DEV)
+    n = 90000
+    inc.build(buf[:n])
+    assert inc.incremental_builds == 0
+    q = cloud[::7][:20000].contiguous() + 0.01
+    for step, k in enumerate((1, 777, 20000, 9222, 3000)):
+        if step == 4:
+            buf[n:n + k] = extra
+        inc.build(buf[:n + k], appended_from=n)
+        n += k
+        full = ops.SpatialHash(0.08).build(buf[:n].clone())
+        assert inc.incremental_builds == step + 1
+        assert torch.equal(inc.sorted_pts[:n].view(torch.int32), full.sorted_pts[:n].view(torch.int32))
+        assert torch.equal(inc._keys[:n], full._keys[:n])
+        assert (inc.struct.n, inc.struct.capacity) == (full.struct.n, full.struct.capacity)
+        a = ops.knn_query(inc, q, radius=0.08)
+        b = ops.knn_query(full, q, radius=0.08)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # a caller that does NOT vouch for the old rows gets the full sort
+    inc.build(buf[:n])
+    assert inc.incremental_builds == 5
+
+
 def test_composite_matches_reference_vectors():
     from point_slam_b200 import ops
     z = np.load(C.GOLDEN + '/aux.npz')

@@ -238,5 +238,5 @@ def test_entry_points_reject_null_arguments_without_a_gpu():
     assert b'capacity' in lib.psl_last_error()
     assert lib.psl_feat_scatter(None, 8, 100, None, None, None, None, None, None, None, 0, None) < 0
     assert lib.psl_composite_fwd(None, None, None, 4, 5, 0.1, None, None, None, None, None) < 0
-    assert lib.psl_color_fwd_tc_w16(None, None, None, 4, None, None, None, None, None, None, None, None, None, None, None, None) < 0
+    assert lib.psl_color_fwd_h2(None, None, None, 4, None, None, None, None, None, None, None, None, None, None, None) < 0
     assert lib.psl_add_points_ws_bytes(6000) > 4 * 6000 * 4 and lib.psl_frustum_select_ws_bytes(500000) > 500000 * 5
