@@ -85,7 +85,7 @@ def test_add_neural_points_bookkeeping_with_stubbed_kernels(monkeypatch):
     from point_slam_b200 import ops
     from point_slam_b200.src.neural_point import NeuralPointCloud
 
-    def fake_build(self, cloud_pos):
+    def fake_build(self, cloud_pos, appended_from=0):
         self._cloud = cloud_pos.detach().clone().float().reshape(-1, 3)
         self.n = self._cloud.shape[0]
         return self
@@ -174,7 +174,7 @@ def test_replica_append_points_matches_source_cloud(monkeypatch):
     from point_slam_b200 import ops, parallel as PL
     from point_slam_b200.src.neural_point import NeuralPointCloud
 
-    def fake_build(self, cloud_pos):
+    def fake_build(self, cloud_pos, appended_from=0):
         self._cloud = cloud_pos.detach().clone().float().reshape(-1, 3)
         self.n = self._cloud.shape[0]
         return self
