@@ -110,6 +110,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- geometry branch on the warp-level tensor-core path (psl_geo_mma.cu): data path without parameter gradients -----------------
+// selected by bit 1 of psl_decode_cfg.reserved on a geometry-stage call; the fragment images live behind the FFMA blob in `packed`
+constexpr int PSL_GEO_MMA_BIT = 2;
+constexpr int GEO_MMA_SAVE_WORDS = 5;            // one 32-bit ReLU mask per layer
+size_t geo_mma_floats();
+int geo_mma_pack(const psl_decoder_params* P, float* packed, cudaStream_t st);
+int geo_fwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos, long long m, const int* I, const float* D,
+                const int* nnum, const double* r2, const float* geo_feats, const float* rand_geo, float* raw, unsigned char* has_nb,
+                float* save, cudaStream_t st);
+int geo_bwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos, long long m, const int* I, const float* D,
+                const int* nnum, const double* r2, const float* cloud_pos, const float* geo_feats, const float* save,
+                const float* d_raw, float* d_pos, float* d_cg, float* wn, const float* dwn_extra, const float* dpos_extra,
+                cudaStream_t st);
+
 // IDW weight of one (sample, neighbour) slot before normalisation (decoder.py:152-157)
 __device__ __forceinline__ float idw_raw(float D, int idx, float thr_le, int weighting) {
     if (idx < 0 || !(D <= thr_le)) return 0.f;

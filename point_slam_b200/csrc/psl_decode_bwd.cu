@@ -985,6 +985,12 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
     }
     if (d_exposure_affine) wc = true;
     a.want_geo_params = wg; a.want_col_params = wc && color;
+    if (!color && (cfg->reserved & PSL_GEO_MMA_BIT)) {
+        PSL_REQUIRE(!wg, "the tensor-core geometry backward returns data gradients only (clear bit 1 of cfg.reserved)");
+        PSL_REQUIRE(packed, "NULL argument");
+        return geo_bwd_mma(cfg, packed, pos, m, I, D, nnum, r2, cloud_pos, geo_feats, save, d_raw, d_pos, d_cg, wn, dwn_extra,
+                           dpos_extra, st);
+    }
     const long long n_tiles = (m + TS - 1) / TS;
     const long long grid = bwd_grid(m);
     PSL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_BYTES));

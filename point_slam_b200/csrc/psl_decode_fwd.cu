@@ -343,10 +343,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_decode_fwd(DecodeArgs a, long
 
 using namespace psl;
 
-extern "C" size_t psl_packed_params_floats(void) { return (size_t)PACKED_FLOATS; }
+extern "C" size_t psl_packed_params_floats(void) { return (size_t)PACKED_FLOATS + geo_mma_floats(); }
 
 extern "C" size_t psl_decode_save_floats_per_sample(const psl_decode_cfg* cfg) {
     if (!cfg) return 0;
+    if (cfg->stage == PSL_STAGE_GEOMETRY && (cfg->reserved & PSL_GEO_MMA_BIT)) return (size_t)GEO_MMA_SAVE_WORDS;
     return (size_t)save_layout(cfg->stage == PSL_STAGE_COLOR, cfg->encode_rel_pos).total;
 }
 
@@ -389,10 +390,10 @@ extern "C" int psl_pack_params(const psl_decoder_params* P, float* packed, psl_s
     add_job(J, P->c_Wo, OFF_COL(4) + CL_X(4), 4, 128, 3, 128, 0, 1);
     add_job(J, P->c_bo, OFF_COL(4) + CL_X(4) + 512, 3, 1, 3, 3, 0, 0);
     for (int i = 0; i < J.n; ++i) PSL_REQUIRE(J.j[i].src != nullptr, "NULL parameter pointer");
-    TimingScope ts(T_PACK, st);
+    TimingScope ts(T_PACK, st, 2);
     k_pack<<<dim3(8, J.n), 256, 0, st>>>(J, packed);
     PSL_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return geo_mma_pack(P, packed, st);            // pre-split B fragments of the geometry matrices (psl_geo_mma.cu)
 }
 
 extern "C" int psl_decode_fwd(const psl_decode_cfg* cfg, const float* packed, const float* pos, int64_t m,
@@ -407,6 +408,8 @@ extern "C" int psl_decode_fwd(const psl_decode_cfg* cfg, const float* packed, co
     PSL_REQUIRE(cfg->rgb_mode != PSL_RGB_AFFINE_SIGMOID || exposure_affine, "affine mode needs exposure_affine");
     PSL_REQUIRE(r2 == nullptr || cfg->r2_group >= 1, "r2_group must be >= 1");
     if (m == 0) return 0;
+    if (cfg->stage == PSL_STAGE_GEOMETRY && (cfg->reserved & PSL_GEO_MMA_BIT))
+        return geo_fwd_mma(cfg, packed, pos, m, I, D, nnum, r2, geo_feats, rand_geo, raw, has_nb, save, as_stream(stream));
     DecodeArgs a{};
     a.cfg = *cfg; a.packed = packed; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
     a.cloud_pos = cloud_pos; a.geo_feats = geo_feats; a.col_feats = col_feats; a.rand_geo = rand_geo;

@@ -177,7 +177,7 @@ def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_de
     params = [ops._f32c(p) for p in decoders.kernel_params()]
     depth, var, rgb, _, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg, rc,
                                                 cloud_pos, geo_feats, col_feats, None, True, colour_param_grads=False,
-                                                pack=pack, prepacked=prepacked)
+                                                geo_param_grads=False, pack=pack, prepacked=prepacked)
     d_depth = torch.empty(n, device=device); d_rgb = torch.empty(n, 3, device=device)
     L.check(lib.psl_shell_loss(0, n, L.ptr(depth_in), L.ptr(inside), None, L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(b_color),
                                w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
@@ -228,7 +228,7 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
     depth, var, rgb, ray_mask, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg,
                                                        rc if rc is not None else torch.zeros(32, device=device), cloud_pos,
                                                        fs.npc_geo, fs.npc_col if color else None, None, True,
-                                                       colour_param_grads=color)
+                                                       colour_param_grads=color, geo_param_grads=False)
     d_depth = torch.empty(n, device=device)
     d_rgb = torch.empty(n, 3, device=device) if color else None
     L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),

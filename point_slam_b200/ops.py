@@ -251,6 +251,7 @@ class RenderSettings:
 USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour branch (forward)
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
+USE_GEO_MMA = os.environ.get('PSL_GEO_MMA', '1') != '0'           # geometry branch on mma.sync 3xTF32 when its parameters are frozen
 INCREMENTAL_HASH = os.environ.get('PSL_HASH_APPEND', '1') != '0'   # add_neural_points: sort + merge the new points only (psl_grid_append)
 USE_H2_BACKWARD = os.environ.get('PSL_H2_BWD', '1') != '0'     # f16-plane colour backward with per-row gradient scaling (psl_color_bwd_h2.cu)
 USE_H2_FORWARD = os.environ.get('PSL_H2', '1') != '0'           # f16-plane, two-tiles-in-flight colour forward (psl_color_h2.cu)
@@ -314,7 +315,7 @@ def _default_pack(device):
 
 
 def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
-                    affine, need_grad, colour_param_grads=True, pack=None, prepacked=False):
+                    affine, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False):
     """-> raw, has_nb, save (FFMA layout or None), tsave (tensor-core layout or None), param struct"""
     lib = L.load()
     dev = pos.device
@@ -328,11 +329,16 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
     save = tsave = None
     use_tc = USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance'
+    # geometry branch without parameter gradients (frozen geometry decoder): warp-level tensor-core kernels (psl_geo_mma.cu), which
+    # keep one ReLU mask word per layer for the backward.  The choice travels to the backward in bit 1 of cfg.reserved.
+    if USE_GEO_MMA and not (need_grad and geo_param_grads) and (use_tc or st.stage == 'geometry'):
+        cfg.reserved |= 2
+    geo_bit = cfg.reserved & 2
     # tensor-core backward (data gradients + weight gradients of the colour branch; geometry branch on the FFMA kernel)
     tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and (USE_TC_WGRAD or not colour_param_grads)
     if need_grad:
         scfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 0, cfg.r2_scalar) if tc_bwd else cfg
+                           cfg.is_tracker, geo_bit, cfg.r2_scalar) if tc_bwd else cfg
         per = lib.psl_decode_save_floats_per_sample(C.byref(scfg))
         save = torch.empty(max(M * per, 1), dtype=torch.float32, device=dev)
         if tc_bwd:
@@ -342,7 +348,7 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         # independent (they write different words of `raw`): the geometry kernel runs on a forked stream and fills the SMs
         # the colour kernel's partial last wave leaves idle (25 000 samples = 196 tiles on 148 SMs; tracking: 59 tiles)
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 1, cfg.r2_scalar)       # reserved bit 0: occupancy only, rgb belongs to the colour kernel
+                           cfg.is_tracker, 1 | (geo_bit if (tc_bwd or not need_grad) else 0), cfg.r2_scalar)   # bit 0: occupancy only (rgb belongs to the colour kernel)
         blob = pk.blob
         use_h2 = USE_H2_FORWARD and (tc_bwd or not need_grad)
         if not prepacked:
@@ -432,7 +438,9 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         want_cparams = any(w and name.startswith('c_') for w, name in zip(want, L_PARAM_NAMES))
         grid_a = C.c_int32(0)
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
-                           cfg.is_tracker, 0, cfg.r2_scalar)
+                           cfg.is_tracker, cfg.reserved & 2, cfg.r2_scalar)
+        assert not ((cfg.reserved & 2) and any(w and name.startswith('g_') for w, name in zip(want, L_PARAM_NAMES))), \
+            'the forward kept only ReLU masks of the geometry branch (geo_param_grads=False) but a geometry parameter gradient is requested'
 
         def geometry_backward(dwn_extra, dpos_extra):
             L.check(lib.psl_decode_bwd(C.byref(gcfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
@@ -506,7 +514,7 @@ class RenderSaved:
 
 
 def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo, rand_col,
-                   cloud, geo, col, aff, need_grad, colour_param_grads=True, pack=None, prepacked=False):
+                   cloud, geo, col, aff, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False):
     """Ray-march + kNN -> decode -> composite on contiguous fp32 device tensors, without autograd.
     -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) uint8, RenderSaved (activations only when need_grad)."""
     lib = L.load()
@@ -526,7 +534,7 @@ def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_d
     cfg = st.cfg(S, r2s)
     raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
                                                   rand_col, aff, need_grad, colour_param_grads=colour_param_grads,
-                                                  pack=pack, prepacked=prepacked)
+                                                  geo_param_grads=geo_param_grads, pack=pack, prepacked=prepacked)
     depth = torch.empty((R,), dtype=torch.float32, device=dev)
     var = torch.empty((R,), dtype=torch.float32, device=dev)
     rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
@@ -577,8 +585,10 @@ class _RenderFn(torch.autograd.Function):
         nig = ctx.needs_input_grad
         need_grad = st.grad_mode and any(nig)     # grad mode is sampled by the caller: it is off inside forward()
         cpg = any(n and name.startswith('c_') for n, name in zip(nig[13:], L_PARAM_NAMES)) or bool(nig[12])
+        gpg = any(n and name.startswith('g_') for n, name in zip(nig[13:], L_PARAM_NAMES))
         depth, var, rgb, ray_mask, sv = render_forward(st, grid, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo,
-                                                       rand_col, cloud, geo, col, aff, need_grad, colour_param_grads=cpg)
+                                                       rand_col, cloud, geo, col, aff, need_grad, colour_param_grads=cpg,
+                                                       geo_param_grads=gpg)
         ctx.st, ctx.cfg = st, sv.cfg
         ctx.save_for_backward(*sv.tensors(), *params_c)
         ctx.mark_non_differentiable(ray_mask)
@@ -616,8 +626,9 @@ class _DecodeFn(torch.autograd.Function):
         need_grad = st.grad_mode and any(ctx.needs_input_grad)     # grad mode is sampled by the caller: it is off inside forward()
         nig = ctx.needs_input_grad
         cpg = any(n and name.startswith('c_') for n, name in zip(nig[11:], L_PARAM_NAMES)) or bool(nig[10])
+        gpg = any(n and name.startswith('g_') for n, name in zip(nig[11:], L_PARAM_NAMES))
         raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_pts, cloud, geo, col, rand_geo,
-                                                      rand_col, aff, need_grad, colour_param_grads=cpg)
+                                                      rand_col, aff, need_grad, colour_param_grads=cpg, geo_param_grads=gpg)
         ctx.st, ctx.cfg = st, cfg
         ctx.save_for_backward(pos, I, D, nn, r2_pts, cloud, geo, col, aff, raw, save, tsave, *params_c)
         hb = has_nb.bool()
