@@ -14,11 +14,12 @@
 //     shared by every warp of the SM) -- no shared-memory staging, no CTA barrier anywhere in the kernel;
 //   * kept for the backward: one 32-bit ReLU mask per sample and layer (20 B / sample instead of 1.4 KB).
 #include "psl_decode.cuh"
+#include "psl_tc.cuh"
 
 namespace psl {
 namespace gm {
 
-constexpr int WPB = 4;                                  // warps per block (independent: block size only sets the scheduling grain)
+constexpr int WPB = 12;                                 // warps per block: independent 16-sample tiles sharing one weight image in smem
 constexpr int ROWS = 16;                                // samples per warp tile
 
 // ---- forward blob: [k-step][n-tile 4][lane 32] float4 {b0 hi, b1 hi, b0 lo, b1 lo} --------------------------------------------
@@ -119,7 +120,7 @@ __global__ void k_geo_mma_pack(PackSrc S, float4* __restrict__ dst) {
     pack_items(S, dst, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-// ---- shared by both directions: sample meta of a 16-row warp tile ---------------------------------------------------------------
+// ---- shared by both directions ----------------------------------------------------------------------------------------------------
 struct GeoArgs {
     psl_decode_cfg cfg;
     const float* packed;                 // FFMA blob (biases, embedder matrix, output layer) followed by the fragment images
@@ -134,25 +135,70 @@ struct GeoArgs {
     const float* dwn_extra; const float* dpos_extra;
 };
 
+// Block = WPB independent warps sharing one copy of the direction's fragment image in shared memory (one bulk copy per block,
+// in flight while the warps gather).  Per-warp scratch follows the image.
+constexpr int BLOB_BYTES = FWD_ITEMS * 16;               // both directions: 122 880 B
+static_assert(FWD_ITEMS == BWD_ITEMS, "one shared-memory plan for both directions");
+constexpr int S_GB = BLOB_BYTES;                         // [3][96] embedder matrix
+constexpr int S_BAR = S_GB + 3 * 96 * 4;                 // mbarrier
+constexpr int S_WARP = S_BAR + 16;                       // per-warp scratch from here
+constexpr int FW_WN = 0, FW_I = 128, FW_HAS = 256, FW_WORDS = 272;                                     // forward: 1088 B per warp
+constexpr int BW_WN = 0, BW_WR = 128, BW_DWN = 256, BW_I = 384, BW_P = 512, BW_DP = 576, BW_DEN = 640, BW_HAS = 656,
+              BW_MASK = 672, BW_WORDS = 752;                                                           // backward: 3008 B per warp
+constexpr int SM_GEO_FWD = S_WARP + WPB * FW_WORDS * 4;
+constexpr int SM_GEO_BWD = S_WARP + WPB * BW_WORDS * 4;
+static_assert(SM_GEO_BWD <= 227 * 1024, "shared memory over budget");
+
+// block prologue: thread 0 starts the bulk copy of the fragment image; everybody stages the embedder matrix
+__device__ __forceinline__ void start_image(unsigned char* smem, const float4* __restrict__ image, const float* __restrict__ gB) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S_BAR);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+        tc::mbar_expect_tx(bar, BLOB_BYTES);
+        constexpr int CH = BLOB_BYTES / 8;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) tc::bulk_g2s(smem + c * CH, reinterpret_cast<const unsigned char*>(image) + c * CH, CH, bar);
+    }
+    float* sGB = reinterpret_cast<float*>(smem + S_GB);
+    for (int i = threadIdx.x; i < 3 * 96; i += blockDim.x) sGB[i] = __ldg(gB + i);
+    __syncthreads();                                     // the only block-wide barrier: barrier init + sGB visible
+}
+__device__ __forceinline__ void wait_image(unsigned char* smem) { tc::mbar_wait_wd(reinterpret_cast<uint64_t*>(smem + S_BAR), 0); }
+
 // Fourier embedding argument of channel j for a sample whose position was pre-multiplied by 2 pi (decoder.py:31-34)
-__device__ __forceinline__ float emb_arg(const float* __restrict__ gB, int j, float x, float y, float z) {
-    return fmaf(z, __ldg(gB + 2 * 96 + j), fmaf(y, __ldg(gB + 96 + j), x * __ldg(gB + j)));
+__device__ __forceinline__ float emb_arg(const float* sGB, int j, float x, float y, float z) {
+    return fmaf(z, sGB[2 * 96 + j], fmaf(y, sGB[96 + j], x * sGB[j]));
+}
+// k-step against the shared-memory image (same as kstep, LDS instead of LDG)
+template <int NT>
+__device__ __forceinline__ void kstep_s(float (&acc)[NT][4], float x0, float x1, float x2, float x3, const float4* B, int lane) {
+    uint32_t ah[4], al[4];
+    split(x0, ah[0], al[0]); split(x1, ah[1], al[1]); split(x2, ah[2], al[2]); split(x3, ah[3], al[3]);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const float4 b = B[n * 32 + lane];
+        const uint32_t b0h = __float_as_uint(b.x), b1h = __float_as_uint(b.y), b0l = __float_as_uint(b.z), b1l = __float_as_uint(b.w);
+        mma8(acc[n], al, b0h, b1h);
+        mma8(acc[n], ah, b0l, b1l);
+        mma8(acc[n], ah, b0h, b1h);
+    }
 }
 
 template <bool SAVE>
-__global__ void __launch_bounds__(WPB * 32, 3) k_geo_fwd_mma(GeoArgs a) {
-    __shared__ float sWnAll[WPB][ROWS * 8];
-    __shared__ int sIAll[WPB][ROWS * 8];
-    __shared__ int sHasAll[WPB][ROWS];
+__global__ void __launch_bounds__(WPB * 32, 1) k_geo_fwd_mma(GeoArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const long long M = a.m;
-    const long long m0 = ((long long)blockIdx.x * WPB + warp) * ROWS;
-    if (m0 >= M) return;
-    float* sWn = sWnAll[warp];
-    int* sI = sIAll[warp];
-    int* sHas = sHasAll[warp];
     const float* __restrict__ pk = a.packed + OFF_GEO;
-    const float4* __restrict__ blob = reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS);
+    start_image(smem, reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS), pk + G_B);
+    const long long M = a.m;
+    const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
+    if (m0 >= M) return;
+    const float4* sB = reinterpret_cast<const float4*>(smem);
+    const float* sGB = reinterpret_cast<const float*>(smem + S_GB);
+    float* sWn = reinterpret_cast<float*>(smem + S_WARP) + warp * FW_WORDS + FW_WN;
+    int* sI = reinterpret_cast<int*>(smem + S_WARP) + warp * FW_WORDS + FW_I;
+    int* sHas = reinterpret_cast<int*>(smem + S_WARP) + warp * FW_WORDS + FW_HAS;
 
     // ---- sample meta + normalised IDW weights (decoder.py:152-163) -------------------------------------------------------------
 #pragma unroll
@@ -208,8 +254,6 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_fwd_mma(GeoArgs a) {
             for (int s = 0; s < 4; ++s) { cg[s][2 * r] = __ldg(a.rand_geo + 8 * s + 2 * t); cg[s][2 * r + 1] = __ldg(a.rand_geo + 8 * s + 2 * t + 1); }
         }
     }
-
-    // ---- Fourier embedding sin(2 pi p B), 93 channels (+3 zero), A-fragment order of k-step s: channels 8s+t, 8s+t+4 -------------
     float px[2], py[2], pz[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -217,44 +261,69 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_fwd_mma(GeoArgs a) {
         py[r] = ok[r] ? __fmul_rn(kTwoPi, a.pos[mr[r] * 3 + 1]) : 0.f;
         pz[r] = ok[r] ? __fmul_rn(kTwoPi, a.pos[mr[r] * 3 + 2]) : 0.f;
     }
-    float e[12][4];
+
+    // ---- embedding products of layers 0 and 3 in ONE pass over the 93 (+3 zero) Fourier channels: sin(2 pi p B) is evaluated once,
+    // ---- in the A-fragment order of k-step s (channels 8s+t, 8s+t+4), and never stored ---------------------------------------------
+    float z0[4][4], z3[4][4];
 #pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(pk + G_BIAS + 8 * n) + t);
+        const float2 b3 = __ldg(reinterpret_cast<const float2*>(pk + G_BIAS + 32 * 3 + 8 * n) + t);
+        z0[n][0] = z0[n][2] = b0.x; z0[n][1] = z0[n][3] = b0.y;
+        z3[n][0] = z3[n][2] = b3.x; z3[n][1] = z3[n][3] = b3.y;
+    }
+    wait_image(smem);
+#pragma unroll 1
     for (int s = 0; s < 12; ++s) {
+        float e[4];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int j = 8 * s + t + 4 * c;
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-                e[s][2 * c + r] = j < PSL_GEO_EMB ? sinf(emb_arg(pk + G_B, j, px[r], py[r], pz[r])) : 0.f;
+            for (int r = 0; r < 2; ++r) e[2 * c + r] = j < PSL_GEO_EMB ? sinf(emb_arg(sGB, j, px[r], py[r], pz[r])) : 0.f;
+        }
+        uint32_t ah[4], al[4];
+        split(e[0], ah[0], al[0]); split(e[1], ah[1], al[1]); split(e[2], ah[2], al[2]); split(e[3], ah[3], al[3]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const float4 b = sB[(F_L0 + s) * 128 + n * 32 + lane];
+            const float4 d = sB[(F_L3E + s) * 128 + n * 32 + lane];
+            mma8(z0[n], al, __float_as_uint(b.x), __float_as_uint(b.y));
+            mma8(z3[n], al, __float_as_uint(d.x), __float_as_uint(d.y));
+            mma8(z0[n], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+            mma8(z3[n], ah, __float_as_uint(d.z), __float_as_uint(d.w));
+            mma8(z0[n], ah, __float_as_uint(b.x), __float_as_uint(b.y));
+            mma8(z3[n], ah, __float_as_uint(d.x), __float_as_uint(d.y));
         }
     }
 
-    // ---- trunk ---------------------------------------------------------------------------------------------------------------
+    // ---- trunk (one rolled loop: the code of a layer fits the instruction cache) -----------------------------------------------------
     float h[4][4];
 #pragma unroll
+    for (int n = 0; n < 4; ++n) h[n][0] = h[n][1] = h[n][2] = h[n][3] = 0.f;
+#pragma unroll 1
     for (int i = 0; i < 5; ++i) {
         float z[4][4], fc[4][4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-            const float2 b = __ldg(reinterpret_cast<const float2*>(pk + G_BIAS + 32 * i + 8 * n) + t);
             const float2 bc = __ldg(reinterpret_cast<const float2*>(pk + G_BIASC + 32 * i + 8 * n) + t);
-            z[n][0] = z[n][2] = b.x; z[n][1] = z[n][3] = b.y;
             fc[n][0] = fc[n][2] = bc.x; fc[n][1] = fc[n][3] = bc.y;
-        }
-        if (i == 0 || i == 3) {
-            const float4* B = blob + (i == 0 ? F_L0 : F_L3E) * 128;
-#pragma unroll
-            for (int s = 0; s < 12; ++s) kstep<4>(z, e[s][0], e[s][1], e[s][2], e[s][3], B + s * 128, lane);
+            if (i == 0) { z[n][0] = z0[n][0]; z[n][1] = z0[n][1]; z[n][2] = z0[n][2]; z[n][3] = z0[n][3]; }
+            else if (i == 3) { z[n][0] = z3[n][0]; z[n][1] = z3[n][1]; z[n][2] = z3[n][2]; z[n][3] = z3[n][3]; }
+            else {
+                const float2 b = __ldg(reinterpret_cast<const float2*>(pk + G_BIAS + 32 * i + 8 * n) + t);
+                z[n][0] = z[n][2] = b.x; z[n][1] = z[n][3] = b.y;
+            }
         }
         if (i >= 1) {
-            const float4* B = blob + (i == 1 ? F_L1 : i == 2 ? F_L2 : i == 3 ? F_L3H : F_L4) * 128;
+            const float4* B = sB + (i == 1 ? F_L1 : i == 2 ? F_L2 : i == 3 ? F_L3H : F_L4) * 128;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) kstep<4>(z, PSL_GM_AFRAG(h[s]), B + s * 128, lane);
+            for (int s = 0; s < 4; ++s) kstep_s<4>(z, PSL_GM_AFRAG(h[s]), B + s * 128, lane);
         }
         {
-            const float4* B = blob + (F_FC + 4 * i) * 128;
+            const float4* B = sB + (F_FC + 4 * i) * 128;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) kstep<4>(fc, PSL_GM_AFRAG(cg[s]), B + s * 128, lane);
+            for (int s = 0; s < 4; ++s) kstep_s<4>(fc, PSL_GM_AFRAG(cg[s]), B + s * 128, lane);
         }
         uint32_t mk[2] = {0u, 0u};
 #pragma unroll
@@ -296,19 +365,20 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_fwd_mma(GeoArgs a) {
 // =================================================================================================================================
 // backward (data gradients)
 // =================================================================================================================================
-__global__ void __launch_bounds__(WPB * 32, 3) k_geo_bwd_mma(GeoArgs a) {
-    __shared__ float sWnAll[WPB][ROWS * 8], sWrAll[WPB][ROWS * 8], sDWnAll[WPB][ROWS * 8];
-    __shared__ int sIAll[WPB][ROWS * 8];
-    __shared__ float sPAll[WPB][ROWS * 4], sDPAll[WPB][ROWS * 4], sDenAll[WPB][ROWS];
-    __shared__ int sHasAll[WPB][ROWS];
+__global__ void __launch_bounds__(WPB * 32, 1) k_geo_bwd_mma(GeoArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const long long M = a.m;
-    const long long m0 = ((long long)blockIdx.x * WPB + warp) * ROWS;
-    if (m0 >= M) return;
-    float *sWn = sWnAll[warp], *sWr = sWrAll[warp], *sDWn = sDWnAll[warp], *sP = sPAll[warp], *sDP = sDPAll[warp], *sDen = sDenAll[warp];
-    int *sI = sIAll[warp], *sHas = sHasAll[warp];
     const float* __restrict__ pk = a.packed + OFF_GEO;
-    const float4* __restrict__ blob = reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS) + FWD_ITEMS;
+    start_image(smem, reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS) + FWD_ITEMS, pk + G_B);
+    const long long M = a.m;
+    const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
+    if (m0 >= M) return;
+    const float4* sB = reinterpret_cast<const float4*>(smem);
+    const float* sGB = reinterpret_cast<const float*>(smem + S_GB);
+    float* sw = reinterpret_cast<float*>(smem + S_WARP) + warp * BW_WORDS;
+    float *sWn = sw + BW_WN, *sWr = sw + BW_WR, *sDWn = sw + BW_DWN, *sP = sw + BW_P, *sDP = sw + BW_DP, *sDen = sw + BW_DEN;
+    int *sI = reinterpret_cast<int*>(sw) + BW_I, *sHas = reinterpret_cast<int*>(sw) + BW_HAS;
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sw) + BW_MASK;            // [5][16]
     const bool need_de = a.d_pos != nullptr;          // the embedding gradient only feeds the sample position
 
 #pragma unroll
@@ -345,14 +415,14 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_bwd_mma(GeoArgs a) {
         sP[q] = (m < M && c < 3) ? a.pos[m * 3 + c] : 0.f;
         sDP[q] = (a.dpos_extra && m < M && c < 3) ? a.dpos_extra[m * 3 + c] : 0.f;
     }
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {                          // ReLU masks of the 5 layers x 16 rows
+        const int q = lane + 32 * h;
+        if (q < 80) { const long long m = m0 + (q & 15); sMask[q] = m < M ? __ldg(a.masks + (long long)(q >> 4) * M + m) : 0u; }
+    }
     __syncwarp();
     const long long mr[2] = {m0 + g, m0 + g + 8};
     const bool ok[2] = {mr[0] < M, mr[1] < M};
-    uint32_t mk[5][2];
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) mk[i][r] = ok[r] ? __ldg(a.masks + (long long)i * M + mr[r]) : 0u;
     const float docc[2] = {ok[0] ? a.d_raw[mr[0] * 4 + 3] : 0.f, ok[1] ? a.d_raw[mr[1] * 4 + 3] : 0.f};
 
     // dh4 = Wo^T d occ
@@ -366,23 +436,25 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_bwd_mma(GeoArgs a) {
 #pragma unroll
     for (int n = 0; n < 12; ++n) de[n][0] = de[n][1] = de[n][2] = de[n][3] = 0.f;
 
-#pragma unroll
+    wait_image(smem);
+#pragma unroll 1
     for (int i = 4; i >= 0; --i) {
         const int pfc = i == 4 ? B_FC4 : i == 3 ? B_FC3 : i == 2 ? B_FC2 : i == 1 ? B_FC1 : B_FC0;
         // (a) d c_g += Fc_i^T dh_i
 #pragma unroll
-        for (int s = 0; s < 4; ++s) kstep<4>(dcg, PSL_GM_AFRAG(dh[s]), blob + (pfc + 4 * s) * 32, lane);
+        for (int s = 0; s < 4; ++s) kstep_s<4>(dcg, PSL_GM_AFRAG(dh[s]), sB + (pfc + 4 * s) * 32, lane);
         // (b) dz_i = dh_i * relu'(z_i)
+        const uint32_t mk[2] = {sMask[i * 16 + g], sMask[i * 16 + g + 8]};
 #pragma unroll
         for (int n = 0; n < 4; ++n)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (!((mk[i][c >> 1] >> (8 * n + 2 * t + (c & 1))) & 1u)) dh[n][c] = 0.f;
+                if (!((mk[c >> 1] >> (8 * n + 2 * t + (c & 1))) & 1u)) dh[n][c] = 0.f;
         // (c) embedding part of the input (layers 0 and 3)
         if (need_de && (i == 0 || i == 3)) {
             const int pe = i == 3 ? B_E3 : B_E0;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) kstep<12>(de, PSL_GM_AFRAG(dh[s]), blob + (pe + 12 * s) * 32, lane);
+            for (int s = 0; s < 4; ++s) kstep_s<12>(de, PSL_GM_AFRAG(dh[s]), sB + (pe + 12 * s) * 32, lane);
         }
         // (d) dh_{i-1} = W_i[:, hidden]^T dz_i
         if (i >= 1) {
@@ -391,7 +463,7 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_bwd_mma(GeoArgs a) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) dn[n][0] = dn[n][1] = dn[n][2] = dn[n][3] = 0.f;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) kstep<4>(dn, PSL_GM_AFRAG(dh[s]), blob + (ph + 4 * s) * 32, lane);
+            for (int s = 0; s < 4; ++s) kstep_s<4>(dn, PSL_GM_AFRAG(dh[s]), sB + (ph + 4 * s) * 32, lane);
 #pragma unroll
             for (int n = 0; n < 4; ++n) { dh[n][0] = dn[n][0]; dh[n][1] = dn[n][1]; dh[n][2] = dn[n][2]; dh[n][3] = dn[n][3]; }
         }
@@ -411,7 +483,7 @@ __global__ void __launch_bounds__(WPB * 32, 3) k_geo_bwd_mma(GeoArgs a) {
             for (int c = 0; c < 2; ++c) {
                 const int j = 8 * n + 2 * t + c;
                 if (j < PSL_GEO_EMB) {
-                    const float b0 = __ldg(pk + G_B + j), b1 = __ldg(pk + G_B + 96 + j), b2 = __ldg(pk + G_B + 2 * 96 + j);
+                    const float b0 = sGB[j], b1 = sGB[96 + j], b2 = sGB[2 * 96 + j];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const float da = de[n][2 * r + c] * cosf(fmaf(pz[r], b2, fmaf(py[r], b1, px[r] * b0)));
@@ -523,7 +595,15 @@ int geo_mma_pack(const psl_decoder_params* P, float* packed, cudaStream_t st) {
     return 0;
 }
 
-static unsigned geo_blocks(long long m) { return (unsigned)((m + gm::WPB * gm::ROWS - 1) / (gm::WPB * gm::ROWS)); }
+// launch shape: 16-sample warp tiles spread over all SMs first (the work of a launch is less than one wave: a block's latency is
+// what is timed, and the legacy tensor path is shared by the warps of an SM), at most WPB warps per block
+static void geo_shape(long long m, unsigned* blocks, unsigned* threads) {
+    const long long tiles = (m + gm::ROWS - 1) / gm::ROWS;
+    long long nw = (tiles + sm_count() - 1) / sm_count();
+    nw = nw < 1 ? 1 : (nw > gm::WPB ? gm::WPB : nw);
+    *blocks = (unsigned)((tiles + nw - 1) / nw);
+    *threads = (unsigned)(32 * nw);
+}
 
 int geo_fwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos, long long m, const int* I, const float* D,
                 const int* nnum, const double* r2, const float* geo_feats, const float* rand_geo, float* raw, unsigned char* has_nb,
@@ -531,9 +611,13 @@ int geo_fwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos
     gm::GeoArgs a{};
     a.cfg = *cfg; a.packed = packed; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
     a.geo_feats = geo_feats; a.rand_geo = rand_geo; a.raw = raw; a.has_nb = has_nb; a.masks_out = reinterpret_cast<uint32_t*>(save);
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(gm::k_geo_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm::SM_GEO_FWD));
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(gm::k_geo_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm::SM_GEO_FWD));
+    unsigned nb, nt;
+    geo_shape(m, &nb, &nt);
     TimingScope ts(T_DECODE_FWD, st);
-    if (save) gm::k_geo_fwd_mma<true><<<geo_blocks(m), gm::WPB * 32, 0, st>>>(a);
-    else gm::k_geo_fwd_mma<false><<<geo_blocks(m), gm::WPB * 32, 0, st>>>(a);
+    if (save) gm::k_geo_fwd_mma<true><<<nb, nt, gm::SM_GEO_FWD, st>>>(a);
+    else gm::k_geo_fwd_mma<false><<<nb, nt, gm::SM_GEO_FWD, st>>>(a);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -546,8 +630,11 @@ int geo_bwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos
     a.cfg = *cfg; a.packed = packed; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
     a.cloud_pos = cloud_pos; a.geo_feats = geo_feats; a.masks = reinterpret_cast<const uint32_t*>(save); a.d_raw = d_raw;
     a.d_pos = d_pos; a.d_cg = d_cg; a.wn_out = wn; a.dwn_extra = dwn_extra; a.dpos_extra = dpos_extra;
+    PSL_CHECK_CUDA(cudaFuncSetAttribute(gm::k_geo_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, gm::SM_GEO_BWD));
+    unsigned nb, nt;
+    geo_shape(m, &nb, &nt);
     TimingScope ts(T_DECODE_BWD, st);
-    gm::k_geo_bwd_mma<<<geo_blocks(m), gm::WPB * 32, 0, st>>>(a);
+    gm::k_geo_bwd_mma<<<nb, nt, gm::SM_GEO_BWD, st>>>(a);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -48,7 +48,8 @@ constexpr int ST_BYTES = ST_B2 + 4096;          // 63488
 constexpr int SB_POS = NS * ST_BYTES;           // [128][4] positions of the current tile
 constexpr int SB_VEC = SB_POS + 2048;           // Bc [3][20] (64) | Brel [3][12] (48)
 constexpr int SB_BAR = SB_VEC + 512;
-constexpr int SB_TOTAL = SB_BAR + 128;
+constexpr int SB_IDX = SB_BAR + 128;            // [8][128] neighbour indices of the current tile (-1: no contribution)
+constexpr int SB_TOTAL = SB_IDX + 4096;
 
 struct Args {
     psl_decode_cfg cfg;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sPos = reinterpret_cast<float*>(smem + SB_POS);
     float* sVec = reinterpret_cast<float*>(smem + SB_VEC);
+    int* sIdx = reinterpret_cast<int*>(smem + SB_IDX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SB_BAR);
     uint64_t* staged = bars;            // [NS] workers -> MMA (count 256)
     uint64_t* consumed = bars + NS;     // [NS] MMA -> workers (tcgen05.commit)
@@ -174,6 +176,22 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_tile = tile;
+    };
+    // workers: resolved neighbour indices of `tile` -> sIdx, so that the per-item prefetch starts its gathers from a shared-memory
+    // read instead of a weight -> index -> row chain of three dependent global loads
+    long long ids_tile = -1;
+    auto load_ids = [&](long long tile) {
+        if (tile == ids_tile) return;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = tid; i < 8 * 128; i += NWORK) {
+            const int k = i >> 7, sm = i & 127;
+            const long long m = tile * 128 + sm;
+            int id = -1;
+            if (m < a.m && a.tsave[TL.wnT + (tile * 8 + k) * 128 + sm] != 0.f) id = a.I[m * 8 + k];
+            sIdx[i] = id;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ids_tile = tile;
     };
     // drain TMEM columns [col, col+ncols) of this thread's lane into partial rows (row = channel), both halves of the warp group
     auto drain = [&](uint32_t col, int ncols, float* dst, int ld) {
@@ -371,7 +389,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     r.z1[0] = *reinterpret_cast<const float4*>(z1T); r.z1[1] = *reinterpret_cast<const float4*>(z1T + 4);
                     const long long m = tile * 128 + m0c + s;
                     int id = -1;
-                    if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];
+                    if (tile == ids_tile) id = sIdx[k * 128 + m0c + s];
+                    else if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];     // first item of the next tile: resolved from global
                     r.id = id;
                     r.f4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     r.cx = r.cy = r.cz = 0.f;
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     const int k = (int)(j & 7);
                     const long long tile = u / UPT;
                     const int m0c = (int)(u % UPT) * KC;
-                    if (k == 0) load_pos(tile);
+                    if (k == 0) { load_pos(tile); load_ids(tile); }
                     if (j + 1 < n_items) fetch(j + 1, nxt);
                     unsigned char* st = acquire();
                     float* sA0 = reinterpret_cast<float*>(st + ST_A0);
