@@ -228,13 +228,14 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
     depth, var, rgb, ray_mask, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg,
                                                        rc if rc is not None else torch.zeros(32, device=device), cloud_pos,
                                                        fs.npc_geo, fs.npc_col if color else None, None, True,
-                                                       colour_param_grads=color, geo_param_grads=False)
+                                                       colour_param_grads=color, geo_param_grads=False, pack=fs.pack,
+                                                       prepacked='geometry')
     d_depth = torch.empty(n, device=device)
     d_rgb = torch.empty(n, 3, device=device) if color else None
     L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),
                                L.ptr(b_color), w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
     needs = fs.needs if color else [False] * L.N_PARAMS
-    ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, repack='bwd',
+    ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, pack=fs.pack, repack='bwd',
                         flat_out=fs.flat if color else None,
                         scatter_to=(fs.row_map, fs.u_max, fs.adam_geo.grad, fs.adam_col.grad))
     if not apply_adam:
@@ -518,6 +519,7 @@ class FusedMapper:
                           (ms or {'geometry': self.lrs, 'color': self.lrs}))
         self.loss = torch.zeros((), device=device)
         require_supported(npc.cfg, 'FusedMapper', tracker=False)
+        self.pack = ops.PackedDecoder(device)              # geometry images packed once per frame (frozen), colour images per iteration
         self.u_max = int(u_max)
         self.graphs = {}
         self.key = None
@@ -571,6 +573,7 @@ class FusedMapper:
             for i, kf in enumerate(keyframes):
                 self.keyframes['color'][i].copy_(kf['color']); self.keyframes['depth'][i].copy_(kf['depth'])
                 self.keyframes['c2w'][i].copy_(kf['c2w'][:3, :4]); self.keyframes['dyn_r_query'][i].copy_(kf['dyn_r_query'])
+            self.pack.pack_geometry(self.dec.kernel_params())
         self.adam_geo.reset(); self.adam_col.reset()
         _reset_adam(self.dec_opt)
         off = 0

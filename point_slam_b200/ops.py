@@ -279,6 +279,12 @@ class PackedDecoder:
         self.hblob = torch.empty(lib.psl_h2_blob_bytes(), dtype=torch.uint8, device=device)      # f16 hi/lo planes (psl_color_h2.cu)
         self.bhblob = torch.empty(lib.psl_h2_bwd_blob_bytes(), dtype=torch.uint8, device=device)  # ... of the backward (psl_color_bwd_h2.cu)
 
+    def pack_geometry(self, params):
+        """FFMA blob + geometry fragment images only (render calls then pass prepacked='geometry')."""
+        pstruct = _param_struct([_f32c(p.detach()) for p in params])
+        L.check(L.load().psl_pack_params(C.byref(pstruct), L.ptr(self.packed), L.stream()), 'psl_pack_params')
+        return self
+
     def pack(self, params, backward=True):
         lib = L.load()
         pstruct = _param_struct([_f32c(p.detach()) for p in params])
@@ -323,7 +329,9 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     pk = pack if pack is not None else _default_pack(dev)
     packed = pk.packed
     pstruct = _param_struct(params)
-    if not prepacked:
+    # prepacked: True = every operand image is current; 'geometry' = the FFMA blob + geometry fragment images are (frozen geometry
+    # decoder: packed once per frame), the colour images are rebuilt here; False = rebuild everything
+    if prepacked is False:
         L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
@@ -351,7 +359,7 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
                            cfg.is_tracker, 1 | (geo_bit if (tc_bwd or not need_grad) else 0), cfg.r2_scalar)   # bit 0: occupancy only (rgb belongs to the colour kernel)
         blob = pk.blob
         use_h2 = USE_H2_FORWARD and (tc_bwd or not need_grad)
-        if not prepacked:
+        if prepacked is not True:
             _tc_fold_or_pack(lib, pstruct, blob)
             if use_h2:
                 L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(blob), L.ptr(pk.hblob), L.stream()), 'psl_h2_pack_params')
