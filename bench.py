@@ -22,6 +22,7 @@ data-path collective -> weak scaling; `--share-map` adds the design's one collec
 rank 0 after its map update, point_slam_b200/parallel.py) to every step.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -205,6 +206,7 @@ class GpuScene:
         self.mapper = G.FusedMapper(self.renderer, self.npc, self.decoders, INTR, wl['map'][1], device) if wl['map'] else None
         self.map_ev = []
         self.map_host = []                # host wall time of the same section (it holds the step's host syncs)
+        self.map_parts = []               # ... split into (add_neural_points x2, frustum selection, mapper.begin_frame)
         self.added = 0
         self.channel = None
         self.delta_ev = []
@@ -275,14 +277,18 @@ class GpuScene:
             h0 = time.perf_counter()
             c2w = torch.from_numpy(fh['c2w'][:3, :4].astype(np.float32)).to(d, non_blocking=True)
             n0 = self.map_update(c2w, tr.depth, tr.color)
+            h1 = time.perf_counter()
             cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=c2w)
             # frustum feature selection with the sensor-depth test, Mapper.get_mask_from_c2w (library kernel, one 4-byte D2H)
             idx = self.ops.frustum_select(self.npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
                                           INTR['cx'], INTR['cy'], edge=-4)
+            h2 = time.perf_counter()
             self.mapper.begin_frame(idx, [cur] + self.keyframes)
             e1.record()
             self.map_ev.append((e0, e1))
-            self.map_host.append((time.perf_counter() - h0) * 1e3)
+            h3 = time.perf_counter()
+            self.map_host.append((h3 - h0) * 1e3)
+            self.map_parts.append((round((h1 - h0) * 1e3, 2), round((h2 - h1) * 1e3, 2), round((h3 - h2) * 1e3, 2)))
             g = geo_iters(m_it)
             if graphs:
                 self.mapper.run('geometry', g)
@@ -407,6 +413,15 @@ class RerenderScene:
 
 
 def timed_steps(scene, steps, first, from_host, dist):
+    gc.collect()
+    gc.disable()          # a generation-2 collection inside a step stalls the host between two device syncs of the map update (seen
+    try:                  # as one 20 ms step per run, always at the same step index); both arms time with the collector off
+        return _timed_steps(scene, steps, first, from_host, dist)
+    finally:
+        gc.enable()
+
+
+def _timed_steps(scene, steps, first, from_host, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -553,6 +568,7 @@ def run_ours(args):
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
                    'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
                    'map_update_host_ms_each': map_host_each if map_ms is not None else None,
+                   'map_update_host_parts_ms': scene.map_parts[-2 * args.steps:] if map_ms is not None else None,
                    'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0),
                    'map_delta_ms_per_step': (float(np.mean([a.elapsed_time(b) for a, b in scene.delta_ev[-2 * args.steps:]]))
                                              if getattr(scene, 'delta_ev', None) else None)},
@@ -729,9 +745,11 @@ def cpu_run(name, n_points, steps, warmup):
         threads = pick_threads(lambda k: sc.step(k, 200))
         for k in range(warmup):
             sc.step(k, 200)
+        gc.collect(); gc.disable()
         t0 = time.perf_counter()
         n = sum(sc.step(2 + warmup + k, n_rays) for k in range(steps))
         dt = time.perf_counter() - t0
+        gc.enable()
         what = f'{n_rays} of the {wl["rays"]} rays' if CONFIGS[name]['mode'] == 'render' else f'{n_rays} rays of a 640x480 frame'
         return n / dt, threads, dt, f'{what} x {wl["S"]} samples, forward render'
     r_track, r_map = cpu_sample_sizes(name)
@@ -740,9 +758,11 @@ def cpu_run(name, n_points, steps, warmup):
     threads = pick_threads(lambda k: sc.step(k, 1, 1 if r_map else 0, 500))
     for k in range(warmup):
         sc.step(2 + k, 1, 1 if r_map else 0, 500)
+    gc.collect(); gc.disable()
     t0 = time.perf_counter()
     n = sum(sc.step(2 + warmup + k, r_track, r_map, m_pix) for k in range(steps))
     dt = time.perf_counter() - t0
+    gc.enable()
     desc = f'{r_track} of the {wl["track"][0]} tracking iterations x {wl["track"][1]} rays'
     if r_map:
         desc += (f' + map update + {r_map} of the {wl["map"][0]} mapping iterations x {m_pix} rays ({geo_iters(r_map)} geometry-stage): '

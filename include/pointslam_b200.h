@@ -322,6 +322,17 @@ int psl_depth_gate(const float* b_depth, int32_t n, float* depth_in, uint8_t* in
 int psl_shell_loss(int32_t mode, int32_t n, const float* depth_in, const uint8_t* inside, const uint8_t* ray_mask,
                    const float* depth, const float* var, const float* rgb, const float* b_color, float w_color,
                    float* loss, float* d_depth, float* d_rgb, psl_stream_t stream);
+/* render tail of one optimisation iteration in ONE launch: composite (common.py:298-336, Renderer.py:189-190 masking), ray validity
+ * (decoder.py:200-201, min_count = int(S / 2 + 1)), the loss of psl_shell_loss (mode 0 tracking, 1 mapping; b_color NULL = depth term
+ * only) and the composite backward.  Writes depth / var / rgb / ray_mask (n), loss (1) and d_raw (n * n_samples, 4).
+ * mode 1 runs one thread per ray over many CTAs and reduces the loss in a fixed order through `ws` (psl_render_tail_ws_bytes(n)
+ * bytes, zero-initialised ONCE by the caller: the kernel re-arms its ticket); mode 0 (batch statistic) is a single-CTA launch. */
+size_t psl_render_tail_ws_bytes(int32_t n);
+int psl_render_tail(int32_t mode, int32_t n, int32_t n_samples, float coef, int32_t min_count, const float* raw,
+                    const uint8_t* has_nb, const float* z_vals, const float* depth_in, const uint8_t* inside,
+                    const float* b_color, float w_color, float* depth, float* var, float* rgb, uint8_t* ray_mask,
+                    float* loss, float* d_raw, void* ws, size_t ws_bytes, psl_stream_t stream);
+
 /* chain rule of psl_sample_rays(cam): (d_rays_o, d_rays_d) (n,3) -> d_cam (7) */
 int psl_pose_bwd(const int64_t* pix, int32_t n, int32_t H0, int32_t W0, int32_t win_w, float fx, float fy, float cx, float cy,
                  const float* cam, const float* d_rays_o, const float* d_rays_d, float* d_cam, psl_stream_t stream);

@@ -17,7 +17,7 @@ _ROOT = os.path.dirname(_HERE)
 # PSL_LIB: load another build of the same sources (A/B experiments, e.g. one compiled with -DPSL_PRECISE_TRIG)
 LIB_PATH = os.environ.get('PSL_LIB') or os.path.join(_HERE, 'libpointslam_b200.so')
 SOURCES = ['psl_api.cu', 'psl_grid.cu', 'psl_decode_fwd.cu', 'psl_decode_bwd.cu', 'psl_geo_mma.cu', 'psl_composite.cu', 'psl_color_tc.cu', 'psl_color_tc_w16.cu', 'psl_color_h2.cu', 'psl_color_bwd_h2.cu', 'psl_color_bwd_tc.cu', 'psl_color_bwd_tc_w16.cu', 'psl_wgrad_tc.cu', 'psl_shell.cu', 'psl_map.cu']
-HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_grid.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh', 'psl_color_tc.cuh', 'psl_color_bwd_tc.cuh']
+HEADERS = ['psl_common.cuh', 'psl_decode.cuh', 'psl_grid.cuh', 'psl_tc.cuh', 'psl_tc_layout.cuh', 'psl_color_tc.cuh', 'psl_color_bwd_tc.cuh', 'psl_composite.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']
 
@@ -81,6 +81,8 @@ _SIGS = {
                                   _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_depth_gate': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     'psl_shell_loss': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    'psl_render_tail_ws_bytes': (_sz, [_i32]),
+    'psl_render_tail': (C.c_int, [_i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'psl_pose_bwd': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'psl_adam_rows': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _f32, _f32, _f32, _i32, _vp]),
     'psl_pose_adam': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),

@@ -136,7 +136,7 @@ __device__ __forceinline__ void signal(uint64_t* a_ready) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int SAVE>
-__global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsigned char* __restrict__ hb, long long n_tiles, int tpp) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsigned char* __restrict__ hb, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sVec = reinterpret_cast<float*>(smem + S_VEC);
     float* sRand = reinterpret_cast<float*>(smem + S_RAND);
@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool rel = a.cfg.encode_rel_pos != 0;
     const TSave TL = tsave_layout(a.m, a.cfg.encode_rel_pos);
-    // tpp = tiles per CTA visit: 2 (two tiles in flight) or, when the launch has fewer tiles than SMs, 1 (one tile per SM)
-    const long long n_pairs = (n_tiles + tpp - 1) / tpp;
+    const long long n_pairs = (n_tiles + 1) / 2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
             }
             uint32_t cnt = 0;
             for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                const int ns = (tpp == 2 && 2 * pair + 1 < n_tiles) ? 2 : 1;
+                const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
                 for (int l = 0; l < NLAYER; ++l) {
                     const int ks = h_ks(l), ub = h_unit(l);
                     for (int s = 0; s < ns; ++s)
@@ -207,7 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
             const uint32_t id16 = tc::make_idesc_f16(128, 16, tc::FMT_F16, tc::FMT_F16);
             if (rel) tc::mbar_wait_p(nbrw_full, 0);
             for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                const int ns = (tpp == 2 && 2 * pair + 1 < n_tiles) ? 2 : 1;
+                const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
                 if (rel) {
                     for (int k = 0; k < 8; ++k) {
                         for (int s = 0; s < ns; ++s) {               // z1 = x N1^T   (K = 64, N = 128)
@@ -393,13 +392,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
         };
 
         for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            const int ns = (tpp == 2 && 2 * pair + 1 < n_tiles) ? 2 : 1;
+            const int ns = (2 * pair + 1 < n_tiles) ? 2 : 1;
             bool inb[2], has[2];
             float cacc[2][8];
             // ---- per-row state of the pair's tiles -> shared memory (quarter 0 computes the IDW weights once per row)
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const long long m = (tpp * pair + s) * TM + r;
+                const long long m = (2 * pair + s) * TM + r;
                 inb[s] = s < ns && m < a.m;
                 has[s] = false;
                 if (inb[s]) has[s] = a.nnum[m] >= a.cfg.min_nn;
@@ -424,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
                         const float wn = __fdiv_rn(w[k], den);
                         sWn[(s * 8 + k) * 128 + r] = wn;
                         sIdx[(s * 8 + k) * 128 + r] = w[k] == 0.f ? -1 : idx[k];
-                        if (SAVE == 2) a.tsave[TL.wnT + ((tpp * pair + s) * 8 + k) * 128 + r] = wn;
+                        if (SAVE == 2) a.tsave[TL.wnT + ((2 * pair + s) * 8 + k) * 128 + r] = wn;
                     }
                     sPos[(s * 4 + 0) * 128 + r] = px; sPos[(s * 4 + 1) * 128 + r] = py; sPos[(s * 4 + 2) * 128 + r] = pz;
                 }
@@ -443,7 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
                     // ---- z1 + b1 -> softplus -> planes
                     for (int s = 0; s < ns; ++s) {
                         tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
-                        epilogue128(s, b1, SAVE == 2 ? a.tsave + TL.z1T + (((tpp * pair + s) * 8 + k) * 128) * 128 : nullptr);
+                        epilogue128(s, b1, SAVE == 2 ? a.tsave + TL.z1T + (((2 * pair + s) * 8 + k) * 128) * 128 : nullptr);
                         signal(&a_ready[s]);
                     }
                     // ---- f = D2 / 4096 + b2 ; c += wn_k f ; then the next neighbour's x (or, after the last one, c and the embedding)
@@ -459,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], INV_SCALE2, b2[8 * q + j]);
                         if (SAVE == 2) {
-                            float4* dst = reinterpret_cast<float4*>(a.tsave + TL.f + (((tpp * pair + s) * 128 + r) * 8 + k) * 32 + 8 * q);
+                            float4* dst = reinterpret_cast<float4*>(a.tsave + TL.f + (((2 * pair + s) * 128 + r) * 8 + k) * 32 + 8 * q);
                             dst[0] = make_float4(f[0], f[1], f[2], f[3]);
                             dst[1] = make_float4(f[4], f[5], f[6], f[7]);
                         }
@@ -495,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
                 for (int j = 0; j < 8; ++j) cacc[s][j] = has[s] ? cacc[s][j] : sRand[8 * q + j];
                 if (SAVE == 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a.tsave[TL.cT + ((tpp * pair + s) * 32 + 8 * q + j) * 128 + r] = cacc[s][j];
+                    for (int j = 0; j < 8; ++j) a.tsave[TL.cT + ((2 * pair + s) * 32 + 8 * q + j) * 128 + r] = cacc[s][j];
                 }
                 uint32_t hi[4], lo[4];
 #pragma unroll
@@ -527,7 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
                 for (int s = 0; s < ns; ++s) {
                     tc::mbar_wait_p(&d_ready[s], pd[s]); pd[s] ^= 1; tc::fence_after_sync();
                     epilogue128(s, sVec + V_BIAS + 128 * l,
-                                SAVE == 2 ? a.tsave + TL.zT + (((long long)l * n_tiles + (tpp * pair + s)) * 128) * 128 : nullptr);
+                                SAVE == 2 ? a.tsave + TL.zT + (((long long)l * n_tiles + (2 * pair + s)) * 128) * 128 : nullptr);
                     signal(&a_ready[s]);
                 }
             }
@@ -540,10 +539,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_color_fwd_h2(Args a, const unsi
                     float o[8];
                     tc::tmem_ld8(lb + T_SLOT * s + T_D, o);
                     if (inb[s]) {
-                        const long long m = (tpp * pair + s) * TM + r;
+                        const long long m = (2 * pair + s) * TM + r;
                         float cr = fmaf(o[0], INV_SCALE2, sVec[V_BOUT]), cg = fmaf(o[1], INV_SCALE2, sVec[V_BOUT + 1]),
                               cb = fmaf(o[2], INV_SCALE2, sVec[V_BOUT + 2]);
-                        if (SAVE == 2) *reinterpret_cast<float4*>(a.tsave + TL.outpre + ((tpp * pair + s) * 128 + r) * 4) = make_float4(cr, cg, cb, 0.f);
+                        if (SAVE == 2) *reinterpret_cast<float4*>(a.tsave + TL.outpre + ((2 * pair + s) * 128 + r) * 4) = make_float4(cr, cg, cb, 0.f);
                         if (a.cfg.rgb_mode == PSL_RGB_AFFINE_SIGMOID) {
                             const float* A = sRand + 32;
                             const float r2 = fmaf(cb, A[6], fmaf(cg, A[3], cr * A[0])) + A[9];
@@ -595,18 +594,15 @@ extern "C" int psl_color_fwd_h2(const psl_decode_cfg* cfg, const void* h2_blob, 
     a.cfg = *cfg; a.pos = pos; a.m = m; a.I = I; a.D = D; a.nnum = nnum; a.r2 = r2;
     a.cloud_pos = cloud_pos; a.col_feats = col_feats; a.rand_col = rand_col; a.affine = exposure_affine; a.raw = raw; a.tsave = tsave;
     const long long n_tiles = (m + ctc::TM - 1) / ctc::TM;
-    // two tiles in flight per CTA visit even when that leaves SMs idle (tracking: 59 tiles -> 30 CTAs): one tile per CTA on
-    // 59 SMs measured 9.0 vs 8.7 ms per frame step -- the second tile rides in the bubbles of the first tile's MMA/epilogue chain
-    const int tpp = 2;
-    const long long n_pairs = (n_tiles + tpp - 1) / tpp;
+    const long long n_pairs = (n_tiles + 1) / 2;
     // per launch: the attribute belongs to the device the launch goes to
     PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
     PSL_CHECK_CUDA(cudaFuncSetAttribute(ch2::k_color_fwd_h2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ch2::S_TOTAL));
     const long long grid = n_pairs < sm_count() ? n_pairs : sm_count();
     TimingScope ts(T_COLOR_FWD_TC, as_stream(stream));
     const unsigned char* hb = static_cast<const unsigned char*>(h2_blob);
-    if (tsave) ch2::k_color_fwd_h2<2><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles, tpp);
-    else ch2::k_color_fwd_h2<0><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles, tpp);
+    if (tsave) ch2::k_color_fwd_h2<2><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles);
+    else ch2::k_color_fwd_h2<0><<<(unsigned)grid, ch2::NTHREADS, ch2::S_TOTAL, as_stream(stream)>>>(a, hb, n_tiles);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

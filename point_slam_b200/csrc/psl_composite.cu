@@ -3,11 +3,9 @@
 // (decoder.py:200-201) and the deterministic feature-gradient scatter.
 #include <cub/device/device_radix_sort.cuh>
 
-#include "psl_common.cuh"
+#include "psl_composite.cuh"
 
 namespace psl {
-
-constexpr int MAX_S = 64;
 
 __global__ void k_composite_fwd(const float4* __restrict__ raw, const unsigned char* __restrict__ has_nb,
                                 const float* __restrict__ z_vals, long long R, int S, float coef,
@@ -15,38 +13,10 @@ __global__ void k_composite_fwd(const float4* __restrict__ raw, const unsigned c
                                 float* __restrict__ weights) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    float T = 1.f, wsum = 0.f, A = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-    for (int s = 0; s < S; ++s) {
-        const float4 v = raw[r * S + s];
-        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
-        const float al = sigmoidf_(__fmul_rn(coef, occ));
-        const float w = __fmul_rn(al, T);
-        T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
-        const float z = z_vals[r * S + s];
-        wsum = __fadd_rn(wsum, w);
-        A = __fadd_rn(A, __fmul_rn(w, z));
-        cr = __fadd_rn(cr, __fmul_rn(w, v.x));
-        cg = __fadd_rn(cg, __fmul_rn(w, v.y));
-        cb = __fadd_rn(cb, __fmul_rn(w, v.z));
-        if (weights) weights[r * S + s] = w;
-    }
-    wsum = __fadd_rn(wsum, 1e-10f);
-    const float d = __fdiv_rn(A, wsum);
-    float vv = 0.f, T2 = 1.f;
-    for (int s = 0; s < S; ++s) {
-        const float4 v = raw[r * S + s];
-        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
-        const float al = sigmoidf_(__fmul_rn(coef, occ));
-        const float w = __fmul_rn(al, T2);
-        T2 = __fmul_rn(T2, __fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
-        const float t = __fsub_rn(z_vals[r * S + s], d);
-        vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(w, t), t));
-    }
-    depth[r] = d;
-    var[r] = vv;
-    rgb[r * 3] = __fdiv_rn(cr, wsum);
-    rgb[r * 3 + 1] = __fdiv_rn(cg, wsum);
-    rgb[r * 3 + 2] = __fdiv_rn(cb, wsum);
+    const RayOut o = composite_fwd_ray(raw, has_nb, z_vals, r, S, coef, weights);
+    depth[r] = o.depth;
+    var[r] = o.var;
+    rgb[r * 3] = o.r; rgb[r * 3 + 1] = o.g; rgb[r * 3 + 2] = o.b;
 }
 
 __global__ void k_composite_bwd(const float4* __restrict__ raw, const unsigned char* __restrict__ has_nb,
@@ -55,41 +25,8 @@ __global__ void k_composite_bwd(const float4* __restrict__ raw, const unsigned c
                                 const float* __restrict__ d_rgb, float4* __restrict__ d_raw) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    float al[MAX_S], Tr[MAX_S];
-    float T = 1.f, wsum = 0.f, A = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-    for (int s = 0; s < S; ++s) {
-        const float4 v = raw[r * S + s];
-        const float occ = has_nb[r * S + s] ? v.w : -100.0f;
-        const float a_ = sigmoidf_(coef * occ);
-        al[s] = a_; Tr[s] = T;
-        const float w = a_ * T;
-        T *= (1.0f - a_) + 1e-10f;
-        wsum += w; A += w * z_vals[r * S + s];
-        cr += w * v.x; cg += w * v.y; cb += w * v.z;
-    }
-    wsum += 1e-10f;
-    const float inv = 1.0f / wsum;
-    const float dep = A * inv, Rr = cr * inv, Rg = cg * inv, Rb = cb * inv;
-    const float gv = d_var ? d_var[r] : 0.f;
-    float sw = 0.f;                                   // sum_s w_s (z_s - depth)
-    for (int s = 0; s < S; ++s) sw += al[s] * Tr[s] * (z_vals[r * S + s] - dep);
-    const float gd = (d_depth ? d_depth[r] : 0.f) - 2.0f * gv * sw;
-    const float gr = d_rgb ? d_rgb[r * 3] : 0.f, gg = d_rgb ? d_rgb[r * 3 + 1] : 0.f, gb = d_rgb ? d_rgb[r * 3 + 2] : 0.f;
-    const float dA = gd * inv, dBr = gr * inv, dBg = gg * inv, dBb = gb * inv;
-    const float dWs = -(gd * dep + gr * Rr + gg * Rg + gb * Rb) * inv;
-    float G = 0.f;                                    // sum_{s>j} dT_s * T_s
-    for (int s = S - 1; s >= 0; --s) {
-        const float4 v = raw[r * S + s];
-        const float z = z_vals[r * S + s];
-        const float w = al[s] * Tr[s];
-        const float t = z - dep;
-        const float dw = gv * t * t + dA * z + dBr * v.x + dBg * v.y + dBb * v.z + dWs;
-        const float u = (1.0f - al[s]) + 1e-10f;
-        const float da = dw * Tr[s] - G / u;
-        G += dw * al[s] * Tr[s];
-        const float docc = da * al[s] * (1.0f - al[s]) * coef;
-        d_raw[r * S + s] = make_float4(w * dBr, w * dBg, w * dBb, docc);
-    }
+    composite_bwd_ray(raw, has_nb, z_vals, r, S, coef, d_depth ? d_depth[r] : 0.f, d_var ? d_var[r] : 0.f, d_rgb ? d_rgb[r * 3] : 0.f,
+                      d_rgb ? d_rgb[r * 3 + 1] : 0.f, d_rgb ? d_rgb[r * 3 + 2] : 0.f, d_raw);
 }
 
 __global__ void k_rays_bwd(const float* __restrict__ d_pos, const float* __restrict__ z_vals, long long R, int S,

@@ -3,7 +3,7 @@
 // (Tracker.py:142-148 / Mapper.py:507-513), the tracking / mapping losses WITH their gradients (Tracker.py:158-180,
 // Mapper.py:524-552), the pose chain rule back to [quaternion, T], and Adam on the pose / the selected feature rows
 // (torch.optim.Adam semantics).  Every reduction is a fixed-order tree inside one CTA: results are bit-reproducible.
-#include "psl_common.cuh"
+#include "psl_composite.cuh"
 
 namespace psl {
 
@@ -213,6 +213,131 @@ __global__ void __launch_bounds__(1024, 1) k_shell_loss(int mode, int n, const f
     if (threadIdx.x == 0) loss[0] = d_rgb ? sd + w_color * sc : sd;
 }
 
+// ---- fused render tail: composite -> ray mask -> loss -> composite backward, ONE single-CTA launch ------------------------------------
+// The four stand-alone kernels it replaces (k_composite_fwd, k_ray_mask, k_shell_loss, k_composite_bwd) move < 1 MB each and are
+// pure launch latency inside an iteration graph.  Same per-ray arithmetic (psl_composite.cuh), same thread <-> ray mapping and
+// summation order as k_shell_loss, so loss and gradients are those of the separate kernels.
+__global__ void __launch_bounds__(1024, 1) k_render_tail(int mode, int n, int S, float coef, int min_count,
+                                                         const float4* __restrict__ raw, const unsigned char* __restrict__ has_nb,
+                                                         const float* __restrict__ z_vals, const float* __restrict__ depth_in,
+                                                         const unsigned char* __restrict__ inside, const float* __restrict__ b_color,
+                                                         float w_color, float* __restrict__ depth, float* __restrict__ var,
+                                                         float* __restrict__ rgb, unsigned char* __restrict__ ray_mask,
+                                                         float* __restrict__ loss, float4* __restrict__ d_raw) {
+    __shared__ float sh[32];
+    // phase 1: composite + ray validity
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const RayOut o = composite_fwd_ray(raw, has_nb, z_vals, i, S, coef, nullptr);
+        depth[i] = o.depth; var[i] = o.var;
+        rgb[i * 3] = o.r; rgb[i * 3 + 1] = o.g; rgb[i * 3 + 2] = o.b;
+        int c = 0;
+        for (int s = 0; s < S; ++s) c += has_nb[(long long)i * S + s] ? 1 : 0;
+        ray_mask[i] = c >= min_count;
+    }
+    // (every thread re-reads only the rays it wrote itself: no barrier needed for the global round trip)
+    float thr = 0.f;
+    if (mode == 0) {
+        float a = 0.f, c = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (inside[i]) { a += fabsf(depth_in[i] - depth[i]) / sqrtf(var[i] + 1e-10f); c += 1.f; }
+        const float sa = block_sum(a, sh), sc = block_sum(c, sh);
+        thr = 10.0f * (sa / fmaxf(sc, 1.0f));
+    }
+    float ld = 0.f, lc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = depth[i], g = depth_in[i];
+        bool m = inside[i] && !isnan(d);
+        float gd = 0.f, gc[3] = {0.f, 0.f, 0.f};
+        if (mode == 0) {
+            const float v = var[i];
+            const float inv = 1.0f / sqrtf(v + 1e-10f);
+            const float tmp = fabsf(g - d) * inv;
+            m = m && !isnan(v) && tmp < thr;
+            if (m) {
+                ld += fminf(fmaxf(tmp, 0.f), 1e3f);
+                const float sg = (g > d) ? 1.f : ((g < d) ? -1.f : 0.f);
+                gd = (tmp <= 1e3f) ? -sg * inv : 0.f;
+            }
+        } else {
+            m = m && ray_mask[i];
+            if (m) {
+                ld += fabsf(g - d);
+                gd = (g > d) ? -1.f : ((g < d) ? 1.f : 0.f);
+            }
+        }
+        if (b_color) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float t = b_color[i * 3 + c], r = rgb[i * 3 + c];
+                if (m) {
+                    lc += fabsf(t - r);
+                    gc[c] = (t > r) ? -w_color : ((t < r) ? w_color : 0.f);
+                }
+            }
+        }
+        composite_bwd_ray(raw, has_nb, z_vals, i, S, coef, gd, 0.f, gc[0], gc[1], gc[2], d_raw);
+    }
+    const float sd = block_sum(ld, sh), sc = block_sum(lc, sh);
+    if (threadIdx.x == 0) loss[0] = b_color ? sd + w_color * sc : sd;
+}
+
+// mapping variant, one thread per ray over as many CTAs as the rays need: the mapping loss has no batch statistic (no 10 x mean gate),
+// so a ray's gradient depends on that ray only.  The loss value is reduced in a fixed order: per-block sums -> partial[block], the
+// block that draws the last ticket adds the partials by block index (deterministic whichever block that is) and re-arms the ticket.
+__global__ void __launch_bounds__(128) k_render_tail_map(int n, int S, float coef, int min_count, const float4* __restrict__ raw,
+                                                         const unsigned char* __restrict__ has_nb, const float* __restrict__ z_vals,
+                                                         const float* __restrict__ depth_in, const unsigned char* __restrict__ inside,
+                                                         const float* __restrict__ b_color, float w_color, float* __restrict__ depth,
+                                                         float* __restrict__ var, float* __restrict__ rgb,
+                                                         unsigned char* __restrict__ ray_mask, float* __restrict__ loss,
+                                                         float4* __restrict__ d_raw, float2* __restrict__ partial, unsigned* __restrict__ ticket) {
+    __shared__ float sh[8];
+    __shared__ bool last;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float ld = 0.f, lc = 0.f;
+    if (i < n) {
+        const RayOut o = composite_fwd_ray(raw, has_nb, z_vals, i, S, coef, nullptr);
+        depth[i] = o.depth; var[i] = o.var;
+        rgb[i * 3] = o.r; rgb[i * 3 + 1] = o.g; rgb[i * 3 + 2] = o.b;
+        int c = 0;
+        for (int s = 0; s < S; ++s) c += has_nb[(long long)i * S + s] ? 1 : 0;
+        const bool rm = c >= min_count;
+        ray_mask[i] = rm;
+        const float d = o.depth, g = depth_in[i];
+        const bool m = inside[i] && !isnan(d) && rm;
+        float gd = 0.f, gc[3] = {0.f, 0.f, 0.f};
+        if (m) {
+            ld = fabsf(g - d);
+            gd = (g > d) ? -1.f : ((g < d) ? 1.f : 0.f);
+            if (b_color) {
+                const float pr[3] = {o.r, o.g, o.b};
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    const float t = b_color[i * 3 + c3];
+                    lc += fabsf(t - pr[c3]);
+                    gc[c3] = (t > pr[c3]) ? -w_color : ((t < pr[c3]) ? w_color : 0.f);
+                }
+            }
+        }
+        composite_bwd_ray(raw, has_nb, z_vals, i, S, coef, gd, 0.f, gc[0], gc[1], gc[2], d_raw);
+    }
+    for (int o = 16; o; o >>= 1) { ld += __shfl_xor_sync(0xffffffffu, ld, o); lc += __shfl_xor_sync(0xffffffffu, lc, o); }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = ld; sh[4 + (threadIdx.x >> 5)] = lc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = make_float2((sh[0] + sh[1]) + (sh[2] + sh[3]), (sh[4] + sh[5]) + (sh[6] + sh[7]));
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            float sd = 0.f, sc = 0.f;
+            for (unsigned b = 0; b < gridDim.x; ++b) { const float2 p = __ldcg(partial + b); sd += p.x; sc += p.y; }
+            loss[0] = b_color ? sd + w_color * sc : sd;
+            *ticket = 0u;
+        }
+    }
+}
+
 // ---- pose chain rule: (d_rays_o, d_rays_d) -> d[quat, T] ---------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1) k_pose_bwd(const long long* __restrict__ pix, int n, int H0, int W0, int ww, float fx, float fy,
                                                       float cx, float cy, const float* __restrict__ cam, const float* __restrict__ d_o,
@@ -395,6 +520,34 @@ extern "C" int psl_shell_loss(int32_t mode, int32_t n, const float* depth_in, co
     TimingScope ts(T_SHELL, as_stream(stream));
     k_shell_loss<<<1, 1024, 0, as_stream(stream)>>>(mode, n, depth_in, inside, ray_mask, depth, var, rgb, b_color, w_color, loss,
                                                    d_depth, d_rgb);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t psl_render_tail_ws_bytes(int32_t n) { return 16 + sizeof(float2) * (size_t)((n + 127) / 128); }
+
+extern "C" int psl_render_tail(int32_t mode, int32_t n, int32_t n_samples, float coef, int32_t min_count, const float* raw,
+                               const uint8_t* has_nb, const float* z_vals, const float* depth_in, const uint8_t* inside,
+                               const float* b_color, float w_color, float* depth, float* var, float* rgb, uint8_t* ray_mask,
+                               float* loss, float* d_raw, void* ws, size_t ws_bytes, psl_stream_t stream) {
+    PSL_REQUIRE(raw && has_nb && z_vals && depth_in && inside && depth && var && rgb && ray_mask && loss && d_raw, "NULL argument");
+    PSL_REQUIRE(mode == 0 || mode == 1, "mode: 0 tracking, 1 mapping");
+    PSL_REQUIRE(n >= 1, "no rays");
+    PSL_REQUIRE(n_samples >= 1 && n_samples <= MAX_S, "n_samples > 64 not supported by the composite backward");
+    TimingScope ts(T_SHELL, as_stream(stream));
+    if (mode == 1) {
+        const unsigned nb = (unsigned)((n + 127) / 128);
+        PSL_REQUIRE(ws && ws_bytes >= psl_render_tail_ws_bytes(n), "mapping mode needs the zero-initialised workspace");
+        unsigned* ticket = static_cast<unsigned*>(ws);
+        float2* partial = reinterpret_cast<float2*>(static_cast<unsigned char*>(ws) + 16);
+        k_render_tail_map<<<nb, 128, 0, as_stream(stream)>>>(n, n_samples, coef, min_count, reinterpret_cast<const float4*>(raw), has_nb,
+                                                           z_vals, depth_in, inside, b_color, w_color, depth, var, rgb, ray_mask, loss,
+                                                           reinterpret_cast<float4*>(d_raw), partial, ticket);
+    } else {
+        k_render_tail<<<1, 1024, 0, as_stream(stream)>>>(mode, n, n_samples, coef, min_count, reinterpret_cast<const float4*>(raw), has_nb,
+                                                        z_vals, depth_in, inside, b_color, w_color, depth, var, rgb, ray_mask, loss,
+                                                        reinterpret_cast<float4*>(d_raw));
+    }
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

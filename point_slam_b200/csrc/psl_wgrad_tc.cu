@@ -93,7 +93,8 @@ __device__ __forceinline__ float rows128(float* dstA, const float* __restrict__ 
     return rs;                                      // row sum over the chunk (both threads of a row hold it)
 }
 struct TrunkRegs { float4 h[2], z[2], zp[2], c; };
-struct NbrRegs { float4 dz[2], z1[2], f4, dcc, w4; float cx, cy, cz; int id; };
+struct NbrRegs { float4 dz[2], z1[2], dcc, w4; };
+struct NbrGather { float4 f4; float cx, cy, cz; int id; };      // the neighbour's feature row / position: fetched TWO items ahead
 
 __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -214,9 +215,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
         if (warp < 8) {
             // global operands of item j (unit u0 + j / n_l, layer l_hi - j % n_l), fetched one item ahead of their use
             TrunkRegs cur, nxt;
-            auto fetch = [&](long long j, TrunkRegs& r) {
-                const long long u = u0 + j / n_l;
-                const int l = l_hi - (int)(j % n_l);
+            auto fetch = [&](long long u, int li_, TrunkRegs& r) {
+                const int l = l_hi - li_;
                 const long long tile = u / UPT;
                 const int m0c = (int)(u % UPT) * KC;
                 const int row = tid >> 1, k0 = (tid & 1) * 8;
@@ -230,14 +230,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                 }
                 if (tid < 128) r.c = *reinterpret_cast<const float4*>(a.tsave + TL.cT + tile * 4096 + (tid >> 2) * 128 + m0c + 4 * (tid & 3));
             };
-            if (n_items > 0) fetch(0, cur);
+            if (n_items > 0) fetch(u0, 0, cur);
+            long long u = u0;
+            int li = 0;                                      // item j = (unit u, layer l_hi - li), walked without 64-bit divisions
             for (long long j = 0; j < n_items; ++j) {
-                const long long u = u0 + j / n_l;
-                const int li = (int)(j % n_l), l = l_hi - li;
+                const int l = l_hi - li;
                 const long long tile = u / UPT;
                 const int m0c = (int)(u % UPT) * KC;
                 if (li == 0) load_pos(tile);                 // layers 3 and 0 embed the sample position
-                if (j + 1 < n_items) fetch(j + 1, nxt);
+                const bool wrap = li + 1 == n_l;
+                if (j + 1 < n_items) fetch(u + (wrap ? 1 : 0), wrap ? 0 : li + 1, nxt);
                 const int R = l == 0 ? 80 : 208;             // B rows: l >= 1: [a 128 | c 32 | e 48], l == 0: [e 48 | c 32]
                 const int crow = l == 0 ? 48 : 128;
                 unsigned char* st = acquire();
@@ -287,10 +289,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                 }
                 hand_over();
                 cur = nxt;
+                if (wrap) { li = 0; ++u; } else ++li;
             }
         } else if (lane == 0) {
-            for (long long j = 0; j < n_items; ++j) {
-                const int li = (int)(j % n_l), l = l_hi - li;
+            int li = 0;
+            for (long long j = 0; j < n_items; ++j, li = (li + 1 == n_l) ? 0 : li + 1) {
+                const int l = l_hi - li;
                 const uint32_t base = (uint32_t)(li == 0 ? 0 : (li == 1 ? 192 : 384));
                 const int ncol1 = l == 0 ? 48 : (l == 3 ? 208 : 160);
                 const int R = l == 0 ? 80 : 208, crow = l == 0 ? 48 : 128;
@@ -374,8 +378,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
             if (warp < 8) {
                 const int s = tid & 15, p = tid >> 4;
                 NbrRegs cur, nxt;
-                // global operands of item j (unit u0 + j / 8, neighbour j % 8), fetched one item ahead (the neighbour's feature row
-                // and position need its index first: that dependent chain is what the prefetch hides)
+                NbrGather gcur, gnxt, gnx2;
+                // global operands of item j (unit u0 + j / 8, neighbour j % 8).  The dense planes are fetched one item ahead; the
+                // neighbour's feature row and position -- an index read followed by a scattered, DRAM-latency gather -- two items ahead
                 auto fetch = [&](long long j, NbrRegs& r) {
                     const long long u = u0 + (j >> 3);
                     const int k = (int)(j & 7);
@@ -387,10 +392,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     const float* wnT = a.tsave + TL.wnT + (tile * 8 + k) * 128;
                     r.dz[0] = *reinterpret_cast<const float4*>(dz1T); r.dz[1] = *reinterpret_cast<const float4*>(dz1T + 4);
                     r.z1[0] = *reinterpret_cast<const float4*>(z1T); r.z1[1] = *reinterpret_cast<const float4*>(z1T + 4);
+                    if (tid < 128) {
+                        r.dcc = *reinterpret_cast<const float4*>(a.tbwd + BL.dccT + tile * 4096 + (tid >> 2) * 128 + m0c + 4 * (tid & 3));
+                        r.w4 = *reinterpret_cast<const float4*>(wnT + m0c + 4 * (tid & 3));
+                    }
+                };
+                auto gather = [&](long long j, NbrGather& r) {
+                    const long long u = u0 + (j >> 3);
+                    const int k = (int)(j & 7);
+                    const long long tile = u / UPT;
+                    const int m0c = (int)(u % UPT) * KC;
                     const long long m = tile * 128 + m0c + s;
                     int id = -1;
                     if (tile == ids_tile) id = sIdx[k * 128 + m0c + s];
-                    else if (m < a.m && wnT[m0c + s] != 0.f) id = a.I[m * 8 + k];     // first item of the next tile: resolved from global
+                    else if (m < a.m && a.tsave[TL.wnT + (tile * 8 + k) * 128 + m0c + s] != 0.f) id = a.I[m * 8 + k];   // items of the next tile
                     r.id = id;
                     r.f4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     r.cx = r.cy = r.cz = 0.f;
@@ -398,12 +413,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                         if (p < 8) r.f4 = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)id * 32) + p);
                         if (p < 10) { r.cx = __ldg(a.cloud_pos + (size_t)id * 3); r.cy = __ldg(a.cloud_pos + (size_t)id * 3 + 1); r.cz = __ldg(a.cloud_pos + (size_t)id * 3 + 2); }
                     }
-                    if (tid < 128) {
-                        r.dcc = *reinterpret_cast<const float4*>(a.tbwd + BL.dccT + tile * 4096 + (tid >> 2) * 128 + m0c + 4 * (tid & 3));
-                        r.w4 = *reinterpret_cast<const float4*>(wnT + m0c + 4 * (tid & 3));
-                    }
                 };
-                if (n_items > 0) fetch(0, cur);
+                if (n_items > 0) { fetch(0, cur); gather(0, gcur); }
+                if (n_items > 1) gather(1, gnxt);
                 for (long long j = 0; j < n_items; ++j) {
                     const long long u = u0 + (j >> 3);
                     const int k = (int)(j & 7);
@@ -411,6 +423,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     const int m0c = (int)(u % UPT) * KC;
                     if (k == 0) { load_pos(tile); load_ids(tile); }
                     if (j + 1 < n_items) fetch(j + 1, nxt);
+                    if (j + 2 < n_items) gather(j + 2, gnx2);
                     unsigned char* st = acquire();
                     float* sA0 = reinterpret_cast<float*>(st + ST_A0);
                     float* sA1 = reinterpret_cast<float*>(st + ST_A1);
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     {   // B (64 rows x 16 samples) = x_k^T : thread (sample s = tid % 16, part p = tid / 16):
                         // p < 8: feature float4 p (rows 20 + 4p ..), p < 10: sin/cos j = p (rows p, 10 + p), p >= 10: zero rows 52..63
                         if (p < 8) {
-                            const float fv[4] = {cur.f4.x, cur.f4.y, cur.f4.z, cur.f4.w};
+                            const float fv[4] = {gcur.f4.x, gcur.f4.y, gcur.f4.z, gcur.f4.w};
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 float hi, lo;
@@ -443,11 +456,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                         }
                         if (p < 10) {
                             float sn = 0.f, cs = 0.f;
-                            if (cur.id >= 0) {
+                            if (gcur.id >= 0) {
                                 const float* pp = sPos + (m0c + s) * 4;
-                                const float rx = __fmul_rn(kTwoPi, __fsub_rn(cur.cx, pp[0]));
-                                const float ry = __fmul_rn(kTwoPi, __fsub_rn(cur.cy, pp[1]));
-                                const float rz = __fmul_rn(kTwoPi, __fsub_rn(cur.cz, pp[2]));
+                                const float rx = __fmul_rn(kTwoPi, __fsub_rn(gcur.cx, pp[0]));
+                                const float ry = __fmul_rn(kTwoPi, __fsub_rn(gcur.cy, pp[1]));
+                                const float rz = __fmul_rn(kTwoPi, __fsub_rn(gcur.cz, pp[2]));
                                 sincos_embed(fmaf(rz, sVec[64 + 24 + p], fmaf(ry, sVec[64 + 12 + p], rx * sVec[64 + p])), &sn, &cs);
                             }
                             float hi, lo;
@@ -472,6 +485,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tc(Args a, long long n_tiles)
                     }
                     hand_over();
                     cur = nxt;
+                    gcur = gnxt; gnxt = gnx2;
                 }
             } else if (lane == 0) {
                 for (long long j = 0; j < n_items; ++j) {

@@ -17,6 +17,13 @@ from . import ops
 from .src import common
 
 
+import os as _os
+# composite + ray mask + loss + composite backward as one launch (psl_render_tail).  Mapping: one thread per ray over many CTAs.
+# Tracking needs the batch mean of the gate first -> single-CTA kernel, which measured SLOWER than the four small kernels (39 vs
+# ~25 us per iteration at 1500 rays): off by default.
+FUSED_TAIL = _os.environ.get('PSL_FUSED_TAIL', '1') != '0'
+FUSED_TAIL_TRACKER = _os.environ.get('PSL_FUSED_TAIL_TRACKER', '0') != '0'
+
 def _masked_stats(depth, valid):
     """10*median and 1.2*max of the valid depths (Tracker.py:142-143 / Mapper.py:507-509) without compaction."""
     nan = torch.full_like(depth, float('nan'))
@@ -177,10 +184,14 @@ def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_de
     params = [ops._f32c(p) for p in decoders.kernel_params()]
     depth, var, rgb, _, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg, rc,
                                                 cloud_pos, geo_feats, col_feats, None, True, colour_param_grads=False,
-                                                geo_param_grads=False, pack=pack, prepacked=prepacked)
-    d_depth = torch.empty(n, device=device); d_rgb = torch.empty(n, 3, device=device)
-    L.check(lib.psl_shell_loss(0, n, L.ptr(depth_in), L.ptr(inside), None, L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(b_color),
-                               w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
+                                                geo_param_grads=False, pack=pack, prepacked=prepacked,
+                                                tail=dict(mode=0, depth_in=depth_in, inside=inside, b_color=b_color, w_color=w_color,
+                                                          loss_out=loss_out) if FUSED_TAIL_TRACKER else None)
+    d_depth = d_rgb = None
+    if not FUSED_TAIL_TRACKER:
+        d_depth = torch.empty(n, device=device); d_rgb = torch.empty(n, 3, device=device)
+        L.check(lib.psl_shell_loss(0, n, L.ptr(depth_in), L.ptr(inside), None, L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(b_color),
+                                   w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
     d_o, d_d, _, _, _, _ = ops.render_backward(sv, d_depth, None, d_rgb, True, True, False, False, False, [False] * L.N_PARAMS,
                                                pack=pack, repack=False if prepacked else True)
     L.check(lib.psl_pose_bwd(L.ptr(pix), n, H0, W0, ww, intr['fx'], intr['fy'], intr['cx'], intr['cy'], L.ptr(cam), L.ptr(d_o),
@@ -229,11 +240,15 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
                                                        rc if rc is not None else torch.zeros(32, device=device), cloud_pos,
                                                        fs.npc_geo, fs.npc_col if color else None, None, True,
                                                        colour_param_grads=color, geo_param_grads=False, pack=fs.pack,
-                                                       prepacked='geometry')
-    d_depth = torch.empty(n, device=device)
-    d_rgb = torch.empty(n, 3, device=device) if color else None
-    L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),
-                               L.ptr(b_color), w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
+                                                       prepacked='geometry',
+                                                       tail=dict(mode=1, depth_in=depth_in, inside=inside, b_color=b_color if color else None,
+                                                                 w_color=w_color, loss_out=loss_out) if FUSED_TAIL else None)
+    d_depth = d_rgb = None
+    if not FUSED_TAIL:
+        d_depth = torch.empty(n, device=device)
+        d_rgb = torch.empty(n, 3, device=device) if color else None
+        L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),
+                                   L.ptr(b_color), w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
     needs = fs.needs if color else [False] * L.N_PARAMS
     ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, pack=fs.pack, repack='bwd',
                         flat_out=fs.flat if color else None,

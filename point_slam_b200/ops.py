@@ -521,10 +521,26 @@ class RenderSaved:
         return tuple(getattr(self, k) for k in self.FIELDS)
 
 
+_TAIL_WS = {}
+
+
+def _tail_ws(dev, nbytes):
+    """Zero-initialised ticket + per-block partials of psl_render_tail (the kernel re-arms the ticket, so one buffer per device
+    serves every launch on the stream; grown, never shrunk)."""
+    w = _TAIL_WS.get(str(dev))
+    if w is None or w.numel() < nbytes:
+        w = _TAIL_WS[str(dev)] = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=dev)
+    return w
+
+
 def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo, rand_col,
-                   cloud, geo, col, aff, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False):
+                   cloud, geo, col, aff, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False,
+                   tail=None):
     """Ray-march + kNN -> decode -> composite on contiguous fp32 device tensors, without autograd.
-    -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) uint8, RenderSaved (activations only when need_grad)."""
+    -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) uint8, RenderSaved (activations only when need_grad).
+    tail = dict(mode 0 tracking / 1 mapping, depth_in (R,), inside (R,) u8, b_color (R,3) or None, w_color, loss_out ()): composite,
+    ray mask, the iteration's loss and the composite backward run as ONE launch (psl_render_tail); the saved state then carries
+    d_raw and render_backward(sv, None, None, None, ...) starts from it."""
     lib = L.load()
     dev = ro.device
     R, S = ro.shape[0], st.S
@@ -546,11 +562,21 @@ def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_d
     depth = torch.empty((R,), dtype=torch.float32, device=dev)
     var = torch.empty((R,), dtype=torch.float32, device=dev)
     rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
-    L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(depth), L.ptr(var),
-                                  L.ptr(rgb), None, L.stream()), 'psl_composite_fwd')
     ray_mask = torch.empty((R,), dtype=torch.uint8, device=dev)
-    L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
+    d_raw = None
+    if tail is not None:
+        d_raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        ws = _tail_ws(dev, lib.psl_render_tail_ws_bytes(R))
+        L.check(lib.psl_render_tail(int(tail['mode']), R, S, st.coef, int(S / 2 + 1), L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals),
+                                    L.ptr(tail['depth_in']), L.ptr(tail['inside']), L.ptr(tail.get('b_color')), float(tail['w_color']),
+                                    L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(ray_mask), L.ptr(tail['loss_out']), L.ptr(d_raw),
+                                    L.ptr(ws), ws.numel(), L.stream()), 'psl_render_tail')
+    else:
+        L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z_vals), R, S, st.coef, L.ptr(depth), L.ptr(var),
+                                      L.ptr(rgb), None, L.stream()), 'psl_composite_fwd')
+        L.check(lib.psl_ray_mask(L.ptr(has_nb), R, S, int(S / 2 + 1), L.ptr(ray_mask), L.stream()), 'psl_ray_mask')
     saved = RenderSaved(st, cfg, (z_vals, pos, I, D, nn, r2_ray, cloud, geo, col, aff, raw, has_nb, save, tsave), params_c)
+    saved.d_raw = d_raw
     return depth, var, rgb, ray_mask, saved
 
 
@@ -562,9 +588,13 @@ def render_backward(sv: RenderSaved, d_depth, d_var, d_rgb, want_o, want_d, want
     st = sv.st
     R, S = sv.z_vals.shape
     dev = sv.z_vals.device
-    d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
-    L.check(lib.psl_composite_bwd(L.ptr(sv.raw), L.ptr(sv.has_nb), L.ptr(sv.z_vals), R, S, st.coef, L.ptr(d_depth), L.ptr(d_var),
-                                  L.ptr(d_rgb), L.ptr(d_raw), L.stream()), 'psl_composite_bwd')
+    d_raw = getattr(sv, 'd_raw', None)          # already produced by the fused render tail (render_forward(tail=...))
+    if d_raw is None:
+        d_raw = torch.empty((R * S, 4), dtype=torch.float32, device=dev)
+        L.check(lib.psl_composite_bwd(L.ptr(sv.raw), L.ptr(sv.has_nb), L.ptr(sv.z_vals), R, S, st.coef, L.ptr(d_depth), L.ptr(d_var),
+                                      L.ptr(d_rgb), L.ptr(d_raw), L.stream()), 'psl_composite_bwd')
+    else:
+        assert d_depth is None and d_var is None and d_rgb is None, 'the fused render tail already applied the loss gradients'
     want_pos = want_o or want_d
     d_pos, d_geo, d_col, grads, d_aff = _decode_backward(st, sv.cfg, sv.params, needs, sv.pos, sv.I, sv.D, sv.nn, sv.r2_ray,
                                                          sv.cloud, sv.geo, sv.col, sv.aff, sv.raw, sv.save, d_raw, want_pos,

@@ -149,6 +149,42 @@ def _check_loss(mode, color, n, depth_in, inside, ray_mask, depth, var, rgb, b_c
         assert torch.equal(dc, rgb.grad if rgb.grad is not None else torch.zeros_like(dc))
 
 
+@pytest.mark.parametrize('mode,color', [(0, True), (1, True), (1, False)])
+def test_render_tail_equals_the_four_kernels_it_fuses(mode, color):
+    """psl_render_tail == psl_composite_fwd + psl_ray_mask + psl_shell_loss + psl_composite_bwd (same per-ray arithmetic, same
+    summation order): outputs, loss and d_raw, incl. rays without neighbours, NaN depth inputs and rays outside the gate."""
+    from point_slam_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device=DEV).manual_seed(5 + mode)
+    n, S = 4321, 5
+    raw = torch.randn(n * S, 4, device=DEV, generator=g)
+    raw[:, 3] *= 30
+    has_nb = (torch.rand(n * S, device=DEV, generator=g) > 0.2).to(torch.uint8)
+    z = (torch.rand(n, S, device=DEV, generator=g) * 0.1).cumsum(1) + 1.0
+    depth_in = 1.0 + 0.3 * torch.rand(n, device=DEV, generator=g)
+    inside = (torch.rand(n, device=DEV, generator=g) > 0.1).to(torch.uint8)
+    b_color = torch.rand(n, 3, device=DEV, generator=g)
+    f = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=DEV)
+    depth, var, rgb, mask, loss, d_raw = f(n), f(n), f(n, 3), f(n, dt=torch.uint8), f(()), f(n * S, 4)
+    L.check(lib.psl_composite_fwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z), n, S, 0.1, L.ptr(depth), L.ptr(var), L.ptr(rgb), None, L.stream()), 'fwd')
+    L.check(lib.psl_ray_mask(L.ptr(has_nb), n, S, int(S / 2 + 1), L.ptr(mask), L.stream()), 'mask')
+    d_depth, d_rgb = f(n), (f(n, 3) if color else None)
+    L.check(lib.psl_shell_loss(mode, n, L.ptr(depth_in), L.ptr(inside), L.ptr(mask), L.ptr(depth), L.ptr(var), L.ptr(rgb), L.ptr(b_color),
+                               0.3, L.ptr(loss), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'loss')
+    L.check(lib.psl_composite_bwd(L.ptr(raw), L.ptr(has_nb), L.ptr(z), n, S, 0.1, L.ptr(d_depth), None, L.ptr(d_rgb), L.ptr(d_raw), L.stream()), 'bwd')
+    depth2, var2, rgb2, mask2, loss2, d_raw2 = f(n), f(n), f(n, 3), f(n, dt=torch.uint8), f(()), f(n * S, 4)
+    ws = torch.zeros(lib.psl_render_tail_ws_bytes(n), dtype=torch.uint8, device=DEV)
+    for _ in range(2):                                   # second launch: the ticket was re-armed by the first
+        L.check(lib.psl_render_tail(mode, n, S, 0.1, int(S / 2 + 1), L.ptr(raw), L.ptr(has_nb), L.ptr(z), L.ptr(depth_in), L.ptr(inside),
+                                L.ptr(b_color) if color else None, 0.3, L.ptr(depth2), L.ptr(var2), L.ptr(rgb2), L.ptr(mask2), L.ptr(loss2),
+                                L.ptr(d_raw2), L.ptr(ws), ws.numel(), L.stream()), 'tail')
+    torch.cuda.synchronize()
+    assert torch.equal(depth, depth2) and torch.equal(var, var2) and torch.equal(rgb, rgb2) and torch.equal(mask, mask2)
+    assert float((loss - loss2).abs()) <= 1e-6 * float(loss.abs()), (float(loss), float(loss2))
+    assert float(d_raw.abs().max()) > 0
+    assert float((d_raw - d_raw2).abs().max()) <= 1e-6 * float(d_raw.abs().max())
+
+
 def test_pose_bwd_matches_autograd():
     from point_slam_b200.src import common
     from point_slam_b200 import synth
