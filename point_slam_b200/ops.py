@@ -462,6 +462,28 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
         # that the colour kernel's partial last wave leaves idle.
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
+        # everything the side stream will touch is allocated here, on the main stream (the caching allocator ties a block to the
+        # stream that was current when it was allocated)
+        scatter_args = None
+        if want_geo or want_col:
+            ws2_bytes = lib.psl_feat_scatter_ws_bytes(M)
+            ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+            if scatter_to is not None:
+                row_map, n_rows, d_geo, d_col = scatter_to
+                d_geo = d_geo if want_geo else None
+                d_col = d_col if want_col else None
+            else:
+                row_map, n_rows = None, geo.shape[0]
+                d_geo = torch.zeros_like(geo) if want_geo else None
+                d_col = torch.zeros_like(col) if want_col else None
+            scatter_args = (row_map, n_rows, d_geo, d_col, ws2, ws2_bytes)
+
+        def scatter():
+            row_map, n_rows, d_geo, d_col, ws2, ws2_bytes = scatter_args
+            L.check(lib.psl_feat_scatter_mapped(L.ptr(I), M, L.ptr(row_map), n_rows, L.ptr(wn), L.ptr(d_cg),
+                                                L.ptr(d_colpair) if rel else None, None if rel else L.ptr(d_colpair),
+                                                L.ptr(d_geo), L.ptr(d_col), L.ptr(ws2), ws2_bytes, L.stream()), 'psl_feat_scatter')
+
         if side is not None:
             side.wait_stream(main)
         bwd_tc = lib.psl_color_bwd_h2 if USE_H2_BACKWARD else lib.psl_color_bwd_tc
@@ -470,8 +492,16 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
                        L.ptr(tbwd), L.ptr(d_colpair), L.ptr(wn), L.ptr(dwn_col), L.ptr(dpos_col),
                        int(want_cparams or want_affine), C.byref(grid_a), L.stream()), 'psl_color_bwd_tc')
         if side is not None:
+            colour_done = torch.cuda.Event()
+            colour_done.record(main)
             with torch.cuda.stream(side):
                 geometry_backward(None, None)
+                if scatter_args is not None:
+                    # the deterministic feature-gradient scatter (radix sort of the (point, pair) keys + segmented sums) needs the
+                    # colour kernel's per-pair gradients but nothing from the weight-gradient kernel: it runs beside it, in the issue
+                    # slots that latency-bound kernel leaves idle
+                    side.wait_event(colour_done)
+                    scatter()
         if want_cparams or want_affine:
             wsf = lib.psl_wgrad_tc_ws_floats(M)
             wws = torch.empty(wsf, dtype=torch.float32, device=dev)
@@ -482,11 +512,14 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
             main.wait_stream(side)
         else:
             geometry_backward(dwn_col, dpos_col)
-    else:
-        L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
-                                   L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
-                                   L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), L.ptr(wn), L.ptr(d_colpair),
-                                   C.byref(gstruct), L.ptr(d_aff), None, None, L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
+            if scatter_args is not None:
+                scatter()
+        d_geo, d_col = (scatter_args[2], scatter_args[3]) if scatter_args is not None else (None, None)
+        return d_pos, d_geo, d_col, grads, d_aff
+    L.check(lib.psl_decode_bwd(C.byref(cfg), C.byref(pstruct), L.ptr(packed), L.ptr(pos), M, L.ptr(I), L.ptr(D),
+                               L.ptr(nn), L.ptr(r2), L.ptr(cloud_pos), L.ptr(geo), L.ptr(col), L.ptr(affine), L.ptr(raw),
+                               L.ptr(save), L.ptr(d_raw), L.ptr(d_pos), L.ptr(d_cg), L.ptr(wn), L.ptr(d_colpair),
+                               C.byref(gstruct), L.ptr(d_aff), None, None, L.ptr(ws), ws_bytes, L.stream()), 'psl_decode_bwd')
     d_geo = d_col = None
     if want_geo or want_col:
         ws2_bytes = lib.psl_feat_scatter_ws_bytes(M)
