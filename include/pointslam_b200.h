@@ -208,6 +208,12 @@ int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_params* params_h
                    const float* dpos_extra /* (m,3) or NULL: added to d_pos */,
                    void* ws, size_t ws_bytes, psl_stream_t stream);
 
+/* d_pos (m,3) += dpos_add (m,3 or NULL) + the IDW-weight chain rule (d wn -> d D -> d pos, tracker path of decoder.py:143-163)
+ * applied to dwn (m,8).  The chain is linear in d wn: psl_decode_bwd applies it to the geometry branch's own share while the
+ * colour backward runs on another stream, and this pass adds the colour branch's share (its dwn / dpos outputs) afterwards. */
+int psl_idw_chain(const psl_decode_cfg* cfg, const float* pos, int64_t m, const int32_t* I, const float* D, const double* r2,
+                  const float* cloud_pos, const float* dwn, const float* dpos_add, float* d_pos, psl_stream_t stream);
+
 /* deterministic scatter of per-(sample,neighbour) feature gradients into dense (n_points,32) tensors
  * (replaces ATen's sort-based index_put_(accumulate=True) backward of feats[I], decoder.py:164,372).
  * d_geo / d_col must be zero-filled by the caller; either may be NULL. */

@@ -81,6 +81,7 @@ _SIGS = {
                                   _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_depth_gate': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     'psl_shell_loss': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    'psl_idw_chain': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psl_render_tail_ws_bytes': (_sz, [_i32]),
     'psl_render_tail': (C.c_int, [_i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'psl_pose_bwd': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),

@@ -124,6 +124,9 @@ int geo_bwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos
                 const float* d_raw, float* d_pos, float* d_cg, float* wn, const float* dwn_extra, const float* dpos_extra,
                 cudaStream_t st);
 
+int geo_idw_chain(const psl_decode_cfg* cfg, const float* pos, long long m, const int* I, const float* D, const double* r2,
+                  const float* cloud_pos, const float* dwn, const float* dpos_add, float* d_pos, cudaStream_t st);
+
 // IDW weight of one (sample, neighbour) slot before normalisation (decoder.py:152-157)
 __device__ __forceinline__ float idw_raw(float D, int idx, float thr_le, int weighting) {
     if (idx < 0 || !(D <= thr_le)) return 0.f;

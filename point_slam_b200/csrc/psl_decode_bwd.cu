@@ -1037,3 +1037,16 @@ extern "C" int psl_decode_bwd(const psl_decode_cfg* cfg, const psl_decoder_param
     }
     return 0;
 }
+
+// d_pos (m,3) += dpos_add + chain rule of the IDW weights applied to dwn (m,8): the part of the tracker's position gradient that comes
+// from another kernel's gradient on the normalised weights (decoder.py:143-163), as a separate pass so that the two branch backwards
+// can run concurrently (see psl_idw_chain in include/pointslam_b200.h)
+extern "C" int psl_idw_chain(const psl_decode_cfg* cfg, const float* pos, int64_t m, const int32_t* I, const float* D, const double* r2,
+                             const float* cloud_pos, const float* dwn, const float* dpos_add, float* d_pos, psl_stream_t stream) {
+    PSL_REQUIRE(cfg && pos && I && D && cloud_pos && dwn && d_pos, "NULL argument");
+    PSL_REQUIRE(m >= 0, "m < 0");
+    PSL_REQUIRE(r2 == nullptr || cfg->r2_group >= 1, "r2_group must be >= 1");
+    if (m == 0) return 0;
+    return geo_idw_chain(cfg, pos, m, I, D, r2, cloud_pos, dwn, dpos_add, d_pos, as_stream(stream));
+}
+

@@ -582,6 +582,57 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_bwd_mma(GeoArgs a) {
     }
 }
 
+// ---- IDW-weight chain rule alone: d_pos += d_pos_add + (d wn -> d D -> d pos), for the gradient the COLOUR branch put on the
+// normalised weights (tracker, decoder.py:143-163).  The chain is linear in d wn, so the geometry backward applies it to its own
+// d wn while the colour backward runs, and this kernel adds the colour branch's share afterwards (8 lanes per sample).
+__global__ void k_idw_chain(GeoArgs a) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long m = q >> 3;
+    const int k = (int)(q & 7);
+    const bool ok = m < a.m;
+    int idx = -1;
+    float w = 0.f, Dv = 0.f;
+    if (ok) {
+        idx = a.I[m * 8 + k];
+        Dv = a.D[m * 8 + k];
+        const double r2 = a.r2 ? a.r2[m / a.cfg.r2_group] : a.cfg.r2_scalar;
+        w = idw_raw(Dv, idx, thr_le_of(r2), a.cfg.weighting);
+    }
+    float sum = fabsf(w);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float den0 = fmaxf(sum, 1e-12f);
+    const float wn = __fdiv_rn(w, den0);
+    const float den = sum > 1e-12f ? den0 : 0.f;
+    const float dwn = ok ? a.dwn_extra[m * 8 + k] : 0.f;
+    float dot = dwn * wn;
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (a.cfg.is_tracker && ok && idx >= 0 && w != 0.f) {      // mapping: D does not depend on the sample position in the graph
+        const float dw = den > 0.f ? (dwn - dot) / den : dwn / 1e-12f;
+        float dD;
+        if (a.cfg.weighting == PSL_WEIGHT_EXPO) dD = dw * w * (-10.0f / sqrtf(Dv));
+        else dD = -dw * w * w;
+        const float cx = __ldg(a.cloud_pos + (size_t)idx * 3) - a.pos[m * 3];
+        const float cy = __ldg(a.cloud_pos + (size_t)idx * 3 + 1) - a.pos[m * 3 + 1];
+        const float cz = __ldg(a.cloud_pos + (size_t)idx * 3 + 2) - a.pos[m * 3 + 2];
+        gx = -2.0f * dD * cx; gy = -2.0f * dD * cy; gz = -2.0f * dD * cz;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        gx += __shfl_xor_sync(0xffffffffu, gx, o);
+        gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        gz += __shfl_xor_sync(0xffffffffu, gz, o);
+    }
+    if (ok && k < 3) {
+        const float g = k == 0 ? gx : (k == 1 ? gy : gz);
+        a.d_pos[m * 3 + k] += g + (a.dpos_extra ? a.dpos_extra[m * 3 + k] : 0.f);
+    }
+}
+
 }  // namespace gm
 
 // ---- host side (called by psl_pack_params / psl_decode_fwd / psl_decode_bwd) ------------------------------------------------------
@@ -635,6 +686,17 @@ int geo_bwd_mma(const psl_decode_cfg* cfg, const float* packed, const float* pos
     geo_shape(m, &nb, &nt);
     TimingScope ts(T_DECODE_BWD, st);
     gm::k_geo_bwd_mma<<<nb, nt, gm::SM_GEO_BWD, st>>>(a);
+    PSL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int geo_idw_chain(const psl_decode_cfg* cfg, const float* pos, long long m, const int* I, const float* D, const double* r2,
+                  const float* cloud_pos, const float* dwn, const float* dpos_add, float* d_pos, cudaStream_t st) {
+    gm::GeoArgs a{};
+    a.cfg = *cfg; a.pos = pos; a.m = m; a.I = I; a.D = D; a.r2 = r2; a.cloud_pos = cloud_pos; a.dwn_extra = dwn; a.dpos_extra = dpos_add;
+    a.d_pos = d_pos;
+    TimingScope ts(T_DECODE_BWD, st);
+    gm::k_idw_chain<<<(unsigned)((m * 8 + 255) / 256), 256, 0, st>>>(a);
     PSL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

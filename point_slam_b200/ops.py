@@ -457,11 +457,11 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
                                        C.byref(gstruct), None, L.ptr(dwn_extra), L.ptr(dpos_extra), L.ptr(ws), ws_bytes, L.stream()),
                     'psl_decode_bwd[geometry]')
 
-        # Without a position gradient (mapping) the geometry branch needs nothing from the colour branch -- the IDW-weight chain
-        # rule, which consumes the colour branch's d(weights), only feeds d_pos -- so it runs on a forked stream and fills the SMs
-        # that the colour kernel's partial last wave leaves idle.
+        # The geometry branch needs nothing from the colour branch except, for d_pos, the colour branch's gradient on the IDW weights
+        # -- which enters linearly and is added afterwards (psl_idw_chain) -- so it runs on a forked stream and fills the SMs that
+        # the colour kernel's partial last wave leaves idle.
         main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev) if (OVERLAP_BRANCHES and not want_pos) else None
+        side = _side_stream(dev) if OVERLAP_BRANCHES else None
         # everything the side stream will touch is allocated here, on the main stream (the caching allocator ties a block to the
         # stream that was current when it was allocated)
         scatter_args = None
@@ -510,6 +510,11 @@ def _decode_backward(st: RenderSettings, cfg, params, needs, pos, I, D, nn, r2, 
                                      L.stream()), 'psl_wgrad_tc')
         if side is not None:
             main.wait_stream(side)
+            if want_pos:
+                # tracking: the geometry backward applied the IDW chain rule to its own share of d(weights) while the colour kernel
+                # ran; the chain is linear, so the colour branch's share (and its direct d_pos) is added by one small pass
+                L.check(lib.psl_idw_chain(C.byref(gcfg), L.ptr(pos), M, L.ptr(I), L.ptr(D), L.ptr(r2), L.ptr(cloud_pos), L.ptr(dwn_col),
+                                          L.ptr(dpos_col), L.ptr(d_pos), L.stream()), 'psl_idw_chain')
         else:
             geometry_backward(dwn_col, dpos_col)
             if scatter_args is not None:
