@@ -715,7 +715,7 @@ def cpu_sample_sizes(name):
     if wl['mode'] in ('render', 'rerender'):
         return None
     if wl['map']:
-        f = 5                                               # c2: 40 : 60 (25 geometry) -> 8 : 12 (5 geometry)
+        f = 2                                               # c2: 40 : 60 (25 geometry) -> 20 : 30 (13 geometry), ~10 s per sample
         return max(wl['track'][0] // f, 1), max(wl['map'][0] // f, 1)
     return max(wl['track'][0] // 10, 1), 0                  # c4: 200 -> 20 tracking iterations
 

@@ -192,13 +192,17 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_fwd_mma(GeoArgs a) {
     const float* __restrict__ pk = a.packed + OFF_GEO;
     start_image(smem, reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS), pk + G_B);
     const long long M = a.m;
-    const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
-    if (m0 >= M) return;
     const float4* sB = reinterpret_cast<const float4*>(smem);
     const float* sGB = reinterpret_cast<const float*>(smem + S_GB);
     float* sWn = reinterpret_cast<float*>(smem + S_WARP) + warp * FW_WORDS + FW_WN;
     int* sI = reinterpret_cast<int*>(smem + S_WARP) + warp * FW_WORDS + FW_I;
     int* sHas = reinterpret_cast<int*>(smem + S_WARP) + warp * FW_WORDS + FW_HAS;
+    // persistent over the 16-sample tiles: the block's copy of the weight image is loaded once, however large the launch
+    const long long tstep = (long long)gridDim.x * (blockDim.x >> 5);
+#pragma unroll 1
+    for (long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp; tile * ROWS < M; tile += tstep) {
+    const long long m0 = tile * ROWS;
+    __syncwarp();                                        // the previous tile's readers of the per-warp scratch are done
 
     // ---- sample meta + normalised IDW weights (decoder.py:152-163) -------------------------------------------------------------
 #pragma unroll
@@ -360,6 +364,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_fwd_mma(GeoArgs a) {
             else reinterpret_cast<float4*>(a.raw)[mr[r]] = make_float4(0.f, 0.f, 0.f, occ[r] + bo);
         }
     }
+    }   // tile loop
 }
 
 // =================================================================================================================================
@@ -371,8 +376,6 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_bwd_mma(GeoArgs a) {
     const float* __restrict__ pk = a.packed + OFF_GEO;
     start_image(smem, reinterpret_cast<const float4*>(a.packed + PACKED_FLOATS) + FWD_ITEMS, pk + G_B);
     const long long M = a.m;
-    const long long m0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * ROWS;
-    if (m0 >= M) return;
     const float4* sB = reinterpret_cast<const float4*>(smem);
     const float* sGB = reinterpret_cast<const float*>(smem + S_GB);
     float* sw = reinterpret_cast<float*>(smem + S_WARP) + warp * BW_WORDS;
@@ -380,6 +383,11 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_bwd_mma(GeoArgs a) {
     int *sI = reinterpret_cast<int*>(sw) + BW_I, *sHas = reinterpret_cast<int*>(sw) + BW_HAS;
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sw) + BW_MASK;            // [5][16]
     const bool need_de = a.d_pos != nullptr;          // the embedding gradient only feeds the sample position
+    const long long tstep = (long long)gridDim.x * (blockDim.x >> 5);
+#pragma unroll 1
+    for (long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp; tile * ROWS < M; tile += tstep) {
+    const long long m0 = tile * ROWS;
+    __syncwarp();
 
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -580,6 +588,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) k_geo_bwd_mma(GeoArgs a) {
             }
         }
     }
+    }   // tile loop
 }
 
 // ---- IDW-weight chain rule alone: d_pos += d_pos_add + (d wn -> d D -> d pos), for the gradient the COLOUR branch put on the
@@ -652,7 +661,9 @@ static void geo_shape(long long m, unsigned* blocks, unsigned* threads) {
     const long long tiles = (m + gm::ROWS - 1) / gm::ROWS;
     long long nw = (tiles + sm_count() - 1) / sm_count();
     nw = nw < 1 ? 1 : (nw > gm::WPB ? gm::WPB : nw);
-    *blocks = (unsigned)((tiles + nw - 1) / nw);
+    long long nb = (tiles + nw - 1) / nw;
+    if (nb > sm_count()) nb = sm_count();                 // one block per SM (the image takes most of its shared memory): persistent
+    *blocks = (unsigned)nb;
     *threads = (unsigned)(32 * nw);
 }
 

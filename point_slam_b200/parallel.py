@@ -201,10 +201,13 @@ def rerender_frames(renderer, npc, decoders, frames, device, every_frame=1, grou
         d, _, c = renderer.render_img(npc, decoders, f['c2w'], device, 'color', gt_depth=f['depth'], npc_geo_feats=npc.get_geo_feats(),
                                       npc_col_feats=npc.get_col_feats(), dynamic_r_query=f.get('dyn_r_query'),
                                       cloud_pos=npc.cloud_pos_tensor())
-        m = f['depth'] > 0
-        mse = torch.nn.functional.mse_loss(f['color'][m], c[m])
-        acc += torch.stack([-10.0 * torch.log10(mse).double(), torch.abs(f['depth'][m] - d[m].float()).mean().double(),
-                            torch.ones((), dtype=torch.float64, device=device)])
+        # masked means as weighted sums: boolean-mask indexing would cost four device->host syncs (nonzero) per frame and leave
+        # the GPU idle while the host launches the next frame
+        m = (f['depth'] > 0)
+        cnt = m.sum().clamp(min=1).double()
+        mse = (((f['color'] - c.float()) ** 2).sum(-1) * m).sum().double() / (3.0 * cnt)
+        l1 = (torch.abs(f['depth'] - d.float()) * m).sum().double() / cnt
+        acc += torch.stack([-10.0 * torch.log10(mse), l1, torch.ones((), dtype=torch.float64, device=device)])
         outs[sel[k]] = (d, c)
     if world > 1:
         dist.all_reduce(acc, group=group)

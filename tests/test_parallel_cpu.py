@@ -134,3 +134,28 @@ def test_sharding_helpers():
             assert strided == list(range(n))
             sizes = [PL.shard_range(n, r, world)[1] - PL.shard_range(n, r, world)[0] for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_rerender_metrics_match_masked_selection():
+    """rerender_frames computes PSNR / depth L1 over the pixels with sensor depth > 0 (Mapper.py:868-885) as weighted sums (no
+    boolean-mask indexing, i.e. no device->host sync per frame): same numbers as the selection-based definition."""
+    import math
+    import types
+    g = torch.Generator().manual_seed(3)
+    H, W = 24, 32
+    frames, truth = [], []
+    for k in range(3):
+        depth = torch.rand(H, W, generator=g) * 3
+        depth[torch.rand(H, W, generator=g) < 0.2] = 0.0
+        color = torch.rand(H, W, 3, generator=g)
+        rd, rc = depth + 0.05 * torch.randn(H, W, generator=g), (color + 0.03 * torch.randn(H, W, 3, generator=g)).clamp(0, 1)
+        frames.append(dict(c2w=torch.eye(4), depth=depth, color=color, dyn_r_query=None, _out=(rd, rc)))
+        m = depth > 0
+        truth.append((-10.0 * math.log10(float(torch.nn.functional.mse_loss(color[m], rc[m]))), float((depth[m] - rd[m]).abs().mean())))
+    it = iter(frames)
+    renderer = types.SimpleNamespace(render_img=lambda *a, **kw: (lambda f: (f['_out'][0], None, f['_out'][1]))(next(it)))
+    npc = types.SimpleNamespace(get_geo_feats=lambda: None, get_col_feats=lambda: None, cloud_pos_tensor=lambda: None)
+    out = PL.rerender_frames(renderer, npc, None, frames, 'cpu')
+    assert out['frames'] == 3
+    assert abs(out['psnr'] - sum(t[0] for t in truth) / 3) < 1e-4
+    assert abs(out['depth_l1'] - sum(t[1] for t in truth) / 3) < 1e-6
