@@ -717,7 +717,7 @@ def cpu_sample_sizes(name):
     if wl['map']:
         f = 2                                               # c2: 40 : 60 (25 geometry) -> 20 : 30 (13 geometry), ~10 s per sample
         return max(wl['track'][0] // f, 1), max(wl['map'][0] // f, 1)
-    return max(wl['track'][0] // 10, 1), 0                  # c4: 200 -> 20 tracking iterations
+    return max(wl['track'][0] // 3, 1), 0                   # c4: 200 -> 66 tracking iterations (~11 s)
 
 
 def pick_threads(step_fn):
@@ -741,17 +741,18 @@ def cpu_run(name, n_points, steps, warmup):
     if wl['mode'] in ('render', 'rerender'):
         wl = dict(wl, rays=wl.get('rays', 2000))           # re-render: a 2000-ray sample of the image
         sc = CpuRenderScene(wl, n_points, steps + warmup + 2)
-        n_rays = min(wl['rays'], 1000)
+        n_rays = min(wl['rays'], 5000)
+        reps = max(1, int(np.ceil(1.2e6 / (n_rays * wl['S']))))      # ~10 s of host work per step at ~1.2e5 samples/s
         threads = pick_threads(lambda k: sc.step(k, 200))
         for k in range(warmup):
             sc.step(k, 200)
         gc.collect(); gc.disable()
         t0 = time.perf_counter()
-        n = sum(sc.step(2 + warmup + k, n_rays) for k in range(steps))
+        n = sum(sc.step(2 + warmup + k, n_rays) for k in range(steps) for _ in range(reps))
         dt = time.perf_counter() - t0
         gc.enable()
         what = f'{n_rays} of the {wl["rays"]} rays' if CONFIGS[name]['mode'] == 'render' else f'{n_rays} rays of a 640x480 frame'
-        return n / dt, threads, dt, f'{what} x {wl["S"]} samples, forward render'
+        return n / dt, threads, dt, f'{reps} x ({what} x {wl["S"]} samples, forward render)'
     r_track, r_map = cpu_sample_sizes(name)
     sc = CpuScene(wl, n_points, steps + warmup + 2)
     m_pix = wl['map'][1] if wl['map'] else 0
