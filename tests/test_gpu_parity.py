@@ -100,6 +100,29 @@ def test_knn_bit_exact_large_cloud():
     assert torch.equal(n.cpu(), no)
 
 
+def test_knn_distance_ties_resolve_to_the_smaller_index():
+    """Exact distance ties (duplicated cloud points, and points mirrored around the query): the list merge compares the 32-bit
+    distance first and falls back to the index only on equality -- the reported order must be (distance, index) ascending like
+    the oracle's stable sort, for every query."""
+    from point_slam_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    base = torch.rand(4000, 3, generator=g) * 0.5
+    cloud = torch.cat([base, base[:1500], base[200:900]], 0)                  # duplicates at higher indices
+    q = base[::3][:1200].clone()
+    q[::2] += 0.004                                                           # half of the queries sit exactly on cloud points
+    grid = ops.SpatialHash(0.08).build(cloud.to(DEV))
+    D, I, n = ops.knn_query(grid, q.to(DEV), radius=0.08)
+    qf, cf = q.float(), cloud.float()                                         # reference order: canonical fp32 distance, then index
+    dx, dy, dz = (qf[:, None, 0] - cf[None, :, 0]), (qf[:, None, 1] - cf[None, :, 1]), (qf[:, None, 2] - cf[None, :, 2])
+    dist = (dx * dx + dy * dy) + dz * dz
+    order = torch.argsort(dist, dim=1, stable=True)[:, :8]                    # stable: equal distances stay in index order
+    dref = torch.gather(dist, 1, order)
+    inr = dref <= torch.tensor(0.08, dtype=torch.float32) ** 2
+    assert int((dref[:, 1:] == dref[:, :-1]).sum()) > 500                     # the case really has ties
+    assert torch.equal(I.cpu().long(), torch.where(inr, order, torch.full_like(order, -1)))
+    assert torch.equal(D.cpu(), torch.where(inr, dref, torch.full_like(dref, torch.finfo(torch.float32).max)))
+
+
 def test_incremental_hash_append_is_bit_identical_to_full_rebuild():
     """psl_grid_append (sort the new points + stable merge) == psl_grid_sort on the whole cloud: same sorted copy, same keys, same
     neighbours; several appends in a row, including points that fall into already occupied cells (duplicates of old positions)."""
