@@ -114,8 +114,10 @@ class Clocks:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+            ms = os.environ.get('PSL_CLOCKS_MS', '100')
+            self.p = None if ms == '0' else subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                                             '--format=csv,noheader,nounits', '-lms', ms], stdout=self.f,
+                                                            stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -281,7 +283,7 @@ class GpuScene:
             cur = dict(color=tr.color, depth=tr.depth, dyn_r_query=tr.dyn, c2w=c2w)
             # frustum feature selection with the sensor-depth test, Mapper.get_mask_from_c2w (library kernel, one 4-byte D2H)
             idx = self.ops.frustum_select(self.npc.cloud_pos_tensor(), fh['c2w'], tr.depth, INTR['H'], INTR['W'], INTR['fx'], INTR['fy'],
-                                          INTR['cx'], INTR['cy'], edge=-4)
+                                          INTR['cx'], INTR['cy'], edge=-4, reuse=True)
             h2 = time.perf_counter()
             self.mapper.begin_frame(idx, [cur] + self.keyframes)
             e1.record()
@@ -468,11 +470,15 @@ def run_ours(args):
     for k in range(args.warmup):
         scene.step(k, False)
     cap0 = scene.captures()
+    ms0 = torch.cuda.memory_stats(device)
     clocks = Clocks(local) if rank == 0 else None
     ms, samples, per_step = timed_steps(scene, args.steps, args.warmup, False, dist)
     ms_e2e, samples_e2e, per_step_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
     clk = clocks.stop() if clocks else None
     recaptures = scene.captures() - cap0
+    ms1 = torch.cuda.memory_stats(device)
+    alloc_diag = {k: ms1.get(k, 0) - ms0.get(k, 0) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries', 'num_sync_all_streams')}
+    alloc_diag['reserved_GB'] = round(ms1.get('reserved_bytes.all.current', 0) / 1e9, 2)
     map_ms = None
     if getattr(scene, 'map_ev', None):
         map_each = [round(a.elapsed_time(b), 2) for a, b in scene.map_ev[-2 * args.steps:]]
@@ -566,7 +572,7 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
         'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
-                   'graph_recaptures_in_timed_region': recaptures, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
+                   'graph_recaptures_in_timed_region': recaptures, 'allocator_in_timed_region': alloc_diag, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
                    'map_update_host_ms_each': map_host_each if map_ms is not None else None,
                    'map_update_host_parts_ms': scene.map_parts[-2 * args.steps:] if map_ms is not None else None,
                    'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0),
@@ -802,7 +808,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=None, help='timed steps (default: 20 for the c2 frame step of the CUDA arm, else 5)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
@@ -810,6 +816,10 @@ def main():
     ap.add_argument('--share-map', action='store_true', help='N > 1: one scene replicated on every GPU, rank 0 maps and broadcasts the map delta (NCCL) every step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.steps is None:
+        # one host hiccup inside the map update's sync window costs a whole step (~45 ms: see DESIGN.md section 5), so the default
+        # averages over 20 frame steps (1 s of device time) instead of 5
+        args.steps = 20 if (args.impl == 'ours' and args.config == 'c2') else 5
     if args.impl == 'reference':
         run_reference(args)
     else:

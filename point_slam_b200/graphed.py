@@ -166,6 +166,32 @@ def _sample(lib, pix, K, per, H, W, H0, W0, ww, cam, c2w, color, depth, dyn, int
     return rays_o, rays_d, b_color, r2, depth_in, inside
 
 
+def _draw_beside(decoders, stage, device):
+    """decoders.draw_no_neighbor_vectors on the forked stream (same position in the host's RNG call order: the Philox offsets are
+    assigned at call time)."""
+    if not ops.OVERLAP_BRANCHES:
+        return decoders.draw_no_neighbor_vectors(stage, device)
+    main, side = torch.cuda.current_stream(device), ops._side_stream(device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        return decoders.draw_no_neighbor_vectors(stage, device)
+
+
+_ZEROS32 = {}
+
+
+def _zeros32(device):
+    z = _ZEROS32.get(str(device))
+    if z is None:
+        z = _ZEROS32[str(device)] = torch.zeros(32, device=device)
+    return z
+
+
+def _join_side(device):
+    if ops.OVERLAP_BRANCHES:
+        torch.cuda.current_stream(device).wait_stream(ops._side_stream(device))
+
+
 def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_depth, dyn_r_query, intr, n_pixels, device,
                             geo_feats, col_feats, cloud_pos, edge, loss_out, w_color=0.5, pack=None, prepacked=False, pix=None):
     """tracker_iteration_static on the shell kernels.  cam (7) plain device tensor; writes d_cam (7) and loss_out ().
@@ -177,10 +203,11 @@ def tracker_iteration_fused(renderer, npc, decoders, cam, d_cam, gt_color, gt_de
     if pix is None:
         pix = torch.randint((H - 2 * H0) * ww, (n,), device=device)
     dyn = dyn_r_query if renderer.use_dynamic_radius else None
+    rg, rc = _draw_beside(decoders, 'color', device)           # four tiny RNG kernels: on the forked stream, beside the sampling kernels
     rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, 1, n, H, W, H0, W0, ww, cam, None, gt_color, gt_depth, dyn,
                                                             intr, device)
+    _join_side(device)
     st = _render_settings(renderer, npc, decoders, 'color', True)
-    rg, rc = decoders.draw_no_neighbor_vectors('color', device)
     params = [ops._f32c(p) for p in decoders.kernel_params()]
     depth, var, rgb, _, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg, rc,
                                                 cloud_pos, geo_feats, col_feats, None, True, colour_param_grads=False,
@@ -231,16 +258,17 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
     if pix is None:
         pix = torch.randint(H * W, (K, per), device=device)
     dyn = kfs['dyn_r_query'] if renderer.use_dynamic_radius else None
+    rg, rc = _draw_beside(decoders, stage, device)
     rays_o, rays_d, b_color, r2, depth_in, inside = _sample(lib, pix, K, per, H, W, 0, 0, W, None, kfs['c2w'], kfs['color'],
                                                             kfs['depth'], dyn, intr, device)
+    _join_side(device)
     st = _render_settings(renderer, npc, decoders, stage, False)
-    rg, rc = decoders.draw_no_neighbor_vectors(stage, device)
     params = [ops._f32c(p) for p in decoders.kernel_params()]
     depth, var, rgb, ray_mask, sv = ops.render_forward(st, npc.spatial_hash(), params, rays_o, rays_d, depth_in, None, r2, rg,
-                                                       rc if rc is not None else torch.zeros(32, device=device), cloud_pos,
+                                                       rc if rc is not None else _zeros32(device), cloud_pos,
                                                        fs.npc_geo, fs.npc_col if color else None, None, True,
                                                        colour_param_grads=color, geo_param_grads=False, pack=fs.pack,
-                                                       prepacked='geometry',
+                                                       prepacked='geometry', pack_backward=True,
                                                        tail=dict(mode=1, depth_in=depth_in, inside=inside, b_color=b_color if color else None,
                                                                  w_color=w_color, loss_out=loss_out) if FUSED_TAIL else None)
     d_depth = d_rgb = None
@@ -250,7 +278,7 @@ def mapper_iteration_fused(renderer, npc, decoders, fs, kfs, intr, n_pixels, dev
         L.check(lib.psl_shell_loss(1, n, L.ptr(depth_in), L.ptr(inside), L.ptr(ray_mask), L.ptr(depth), None, L.ptr(rgb),
                                    L.ptr(b_color), w_color, L.ptr(loss_out), L.ptr(d_depth), L.ptr(d_rgb), L.stream()), 'psl_shell_loss')
     needs = fs.needs if color else [False] * L.N_PARAMS
-    ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, pack=fs.pack, repack='bwd',
+    ops.render_backward(sv, d_depth, None, d_rgb, False, False, True, color, False, needs, pack=fs.pack, repack=False,
                         flat_out=fs.flat if color else None,
                         scatter_to=(fs.row_map, fs.u_max, fs.adam_geo.grad, fs.adam_col.grad))
     if not apply_adam:

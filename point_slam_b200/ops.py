@@ -320,6 +320,37 @@ def _default_pack(device):
     return _DEFAULT_PACK[key]
 
 
+def _fwd_flags(st, need_grad, colour_param_grads):
+    """(use_tc, tc_bwd, use_h2) of a decode call -- which kernels run, hence which operand images they need"""
+    use_tc = USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance'
+    tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and (USE_TC_WGRAD or not colour_param_grads)
+    use_h2 = use_tc and USE_H2_FORWARD and (tc_bwd or not need_grad)
+    return use_tc, tc_bwd, use_h2
+
+
+def _pack_images(st, params, pk, prepacked, need_grad, colour_param_grads, backward=False):
+    """Rebuild the operand images a render call needs (on the current stream).  prepacked: False = everything, 'geometry' = the
+    colour images only (the FFMA blob + geometry fragments are current), True = nothing.  backward=True also rebuilds the image of
+    the tensor-core backward (the caller then passes repack=False to render_backward)."""
+    if prepacked is True:
+        return
+    lib = L.load()
+    pstruct = _param_struct(params)
+    if prepacked is False:
+        L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(pk.packed), L.stream()), 'psl_pack_params')
+    use_tc, tc_bwd, use_h2 = _fwd_flags(st, need_grad, colour_param_grads)
+    if use_tc:
+        _tc_fold_or_pack(lib, pstruct, pk.blob)
+        if use_h2:
+            L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(pk.blob), L.ptr(pk.hblob), L.stream()), 'psl_h2_pack_params')
+        if backward and tc_bwd:
+            if USE_H2_BACKWARD:
+                L.check(lib.psl_h2_bwd_pack_params(C.byref(pstruct), L.ptr(pk.blob), L.ptr(pk.bhblob), L.stream()), 'psl_h2_bwd_pack_params')
+            else:
+                L.check(lib.psl_tc_bwd_pack_params(C.byref(pstruct), L.ptr(pk.blob), lib.psl_tc_fold_offset_floats(), L.ptr(pk.bblob),
+                                                   L.stream()), 'psl_tc_bwd_pack_params')
+
+
 def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_pos, geo, col, rand_geo, rand_col,
                     affine, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False):
     """-> raw, has_nb, save (FFMA layout or None), tsave (tensor-core layout or None), param struct"""
@@ -331,19 +362,16 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
     pstruct = _param_struct(params)
     # prepacked: True = every operand image is current; 'geometry' = the FFMA blob + geometry fragment images are (frozen geometry
     # decoder: packed once per frame), the colour images are rebuilt here; False = rebuild everything
-    if prepacked is False:
-        L.check(lib.psl_pack_params(C.byref(pstruct), L.ptr(packed), L.stream()), 'psl_pack_params')
+    _pack_images(st, params, pk, prepacked, need_grad, colour_param_grads)
     raw = torch.empty((M, 4), dtype=torch.float32, device=dev)
     has_nb = torch.empty((M,), dtype=torch.uint8, device=dev)
     save = tsave = None
-    use_tc = USE_TENSOR_CORES and st.stage == 'color' and st.weighting == 'distance'
+    use_tc, tc_bwd, use_h2 = _fwd_flags(st, need_grad, colour_param_grads)
     # geometry branch without parameter gradients (frozen geometry decoder): warp-level tensor-core kernels (psl_geo_mma.cu), which
     # keep one ReLU mask word per layer for the backward.  The choice travels to the backward in bit 1 of cfg.reserved.
     if USE_GEO_MMA and not (need_grad and geo_param_grads) and (use_tc or st.stage == 'geometry'):
         cfg.reserved |= 2
     geo_bit = cfg.reserved & 2
-    # tensor-core backward (data gradients + weight gradients of the colour branch; geometry branch on the FFMA kernel)
-    tc_bwd = use_tc and need_grad and USE_TC_BACKWARD and (USE_TC_WGRAD or not colour_param_grads)
     if need_grad:
         scfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, geo_bit, cfg.r2_scalar) if tc_bwd else cfg
@@ -358,11 +386,6 @@ def _decode_forward(st: RenderSettings, cfg, params, pos, I, D, nn, r2, cloud_po
         gcfg = L.DecodeCfg(L.STAGE['geometry'], cfg.encode_rel_pos, L.RGB_SIGMOID, cfg.weighting, cfg.min_nn, cfg.r2_group,
                            cfg.is_tracker, 1 | (geo_bit if (tc_bwd or not need_grad) else 0), cfg.r2_scalar)   # bit 0: occupancy only (rgb belongs to the colour kernel)
         blob = pk.blob
-        use_h2 = USE_H2_FORWARD and (tc_bwd or not need_grad)
-        if prepacked is not True:
-            _tc_fold_or_pack(lib, pstruct, blob)
-            if use_h2:
-                L.check(lib.psl_h2_pack_params(C.byref(pstruct), L.ptr(blob), L.ptr(pk.hblob), L.stream()), 'psl_h2_pack_params')
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if OVERLAP_BRANCHES else None
         if side is not None:
@@ -573,12 +596,13 @@ def _tail_ws(dev, nbytes):
 
 def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_depth, z_override, r2_ray, rand_geo, rand_col,
                    cloud, geo, col, aff, need_grad, colour_param_grads=True, geo_param_grads=True, pack=None, prepacked=False,
-                   tail=None):
+                   tail=None, pack_backward=False):
     """Ray-march + kNN -> decode -> composite on contiguous fp32 device tensors, without autograd.
     -> depth (R,), var (R,), rgb (R,3), ray_mask (R,) uint8, RenderSaved (activations only when need_grad).
     tail = dict(mode 0 tracking / 1 mapping, depth_in (R,), inside (R,) u8, b_color (R,3) or None, w_color, loss_out ()): composite,
     ray mask, the iteration's loss and the composite backward run as ONE launch (psl_render_tail); the saved state then carries
-    d_raw and render_backward(sv, None, None, None, ...) starts from it."""
+    d_raw and render_backward(sv, None, None, None, ...) starts from it.
+    pack_backward: also rebuild the tensor-core backward's operand image here (then render_backward(..., repack=False))."""
     lib = L.load()
     dev = ro.device
     R, S = ro.shape[0], st.S
@@ -589,11 +613,28 @@ def render_forward(st: RenderSettings, grid: SpatialHash, params_c, ro, rd, gt_d
     D = torch.empty((M, 8), dtype=torch.float32, device=dev)
     nn = torch.empty((M,), dtype=torch.int32, device=dev)
     r2s = float(np.float32(st.radius_query ** 2))
+    if prepacked is not True and OVERLAP_BRANCHES:
+        # the operand images depend on the parameters only, the ray march + kNN on the rays and the cloud only: the (serial, latency-
+        # bound) packing kernels run on the forked stream while the kNN kernel runs, instead of between it and the decode
+        pk = pack if pack is not None else _default_pack(dev)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _pack_images(st, params_c, pk, prepacked, need_grad, colour_param_grads, backward=pack_backward)
+        packed_early = True
+    else:
+        packed_early = False
     L.check(lib.psl_raymarch_knn(C.byref(grid.struct), L.ptr(ro), L.ptr(rd), L.ptr(gt_depth), R, S,
                                  L.ptr(surface_t_vals(S, dev)), st.near_surface, st.far_surface, L.ptr(z_override),
                                  L.ptr(r2_ray), r2s, L.ptr(z_vals), L.ptr(pos), L.ptr(I), L.ptr(D), L.ptr(nn),
                                  L.stream()), 'psl_raymarch_knn')
     cfg = st.cfg(S, r2s)
+    if packed_early:
+        main.wait_stream(side)
+        prepacked = True
+    elif pack_backward:
+        _pack_images(st, params_c, pack if pack is not None else _default_pack(dev), prepacked, need_grad, colour_param_grads, backward=True)
+        prepacked = True
     raw, has_nb, save, tsave, _ = _decode_forward(st, cfg, params_c, pos, I, D, nn, r2_ray, cloud, geo, col, rand_geo,
                                                   rand_col, aff, need_grad, colour_param_grads=colour_param_grads,
                                                   geo_param_grads=geo_param_grads, pack=pack, prepacked=prepacked)
@@ -852,11 +893,17 @@ def add_points(grid: SpatialHash, rays_o, rays_d, gt_depth, gt_color, new_pos: t
     return counts, in_pos, in_rgb
 
 
+_FRUSTUM_SCRATCH = {}
+
+
 def frustum_select(cloud_pos: torch.Tensor, c2w, depth: torch.Tensor, H, W, fx, fy, cx, cy, edge: int = -4,
-                   return_mask: bool = False):
+                   return_mask: bool = False, reuse: bool = False):
     """Mapper.get_mask_from_c2w (Mapper.py:120-168) on the device: -> ascending int64 indices of the selected points
     (a device tensor where the reference returns a Python list; both index the feature tensors the same way).
-    `c2w`: (4,4) or (3,4) pose (tensor / array); it is inverted on the host in float32 like the reference does."""
+    `c2w`: (4,4) or (3,4) pose (tensor / array); it is inverted on the host in float32 like the reference does.
+    reuse=True: outputs and workspace live in a per-device scratch that is kept between calls (the per-frame callers: no allocator
+    traffic between two host syncs of the map update -- an occasional 40 ms stall of one of these allocations was the one outlier
+    step of the bench); the returned index tensor is then a VIEW that the next reuse=True call on the device overwrites."""
     lib = L.load()
     pos = _f32c(cloud_pos).reshape(-1, 3)
     n = pos.shape[0]
@@ -870,14 +917,25 @@ def frustum_select(cloud_pos: torch.Tensor, c2w, depth: torch.Tensor, H, W, fx, 
     depth = depth if torch.is_tensor(depth) else torch.from_numpy(np.ascontiguousarray(depth))
     depth = depth.to(device=dev, dtype=torch.float32).contiguous()
     assert depth.shape == (H, W)
-    mask = torch.empty(n, dtype=torch.uint8, device=dev)
-    idx = torch.empty(n, dtype=torch.int64, device=dev)
-    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.psl_frustum_select_ws_bytes(n) if n else 0
+    if reuse:
+        sc = _FRUSTUM_SCRATCH.get(str(dev))
+        if sc is None or sc['cap'] < n or sc['ws'].numel() < ws_bytes:
+            cap = max(int(n * 1.5), 1024)
+            sc = _FRUSTUM_SCRATCH[str(dev)] = dict(
+                cap=cap, mask=torch.empty(cap, dtype=torch.uint8, device=dev), idx=torch.empty(cap, dtype=torch.int64, device=dev),
+                count=torch.zeros(1, dtype=torch.int32, device=dev),
+                ws=torch.empty(max(lib.psl_frustum_select_ws_bytes(cap), 256), dtype=torch.uint8, device=dev))
+        mask, idx, count, ws = sc['mask'][:n], sc['idx'][:n], sc['count'], sc['ws']
+        count.zero_()
+    else:
+        mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        idx = torch.empty(n, dtype=torch.int64, device=dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     if n:
-        ws_bytes = lib.psl_frustum_select_ws_bytes(n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         L.check(lib.psl_frustum_select(L.ptr(pos), n, w, float(fx), float(fy), float(cx), float(cy), L.ptr(depth), int(H), int(W),
-                                       int(edge), L.ptr(mask), L.ptr(idx), L.ptr(count), L.ptr(ws), ws_bytes, L.stream()),
+                                       int(edge), L.ptr(mask), L.ptr(idx), L.ptr(count), L.ptr(ws), ws.numel(), L.stream()),
                 'psl_frustum_select')
     k = int(count.item())                  # the one synchronisation: the caller sizes its optimisable slices with it
     return (idx[:k], mask.bool()) if return_mask else idx[:k]

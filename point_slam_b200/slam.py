@@ -145,7 +145,7 @@ class PointSLAM:
         # fixed number of frame slots (static shapes of the iteration graph): missing keyframes are filled with the current frame
         kfl = frames + [cur] * (self.n_kf_slots + 1 - len(frames))
         idxs = ops.frustum_select(npc.cloud_pos_tensor(), c2w, depth, I['H'], I['W'], I['fx'], I['fy'], I['cx'], I['cy'],
-                                  edge=m['frustum_edge'])
+                                  edge=m['frustum_edge'], reuse=True)
         if self.mapper is None:
             lr = m['init' if init else 'stage']
             self.mapper = G.FusedMapper(self.r, npc, self.dec, I, m['pixels'], self.dev, w_color=m['w_color_loss'])

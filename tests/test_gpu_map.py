@@ -29,6 +29,10 @@ def test_frustum_select_matches_reference_golden():
     idx = ops.frustum_select(cloud, z['c2w0'][:3], z['depth0'], int(H), int(W), fx, fy, cx, cy, edge=int(z['edge0']))
     assert np.array_equal(idx.cpu().numpy(), z['indices0'])
     assert ops.frustum_select(cloud[:0], z['c2w0'], z['depth0'], int(H), int(W), fx, fy, cx, cy).numel() == 0
+    # reuse=True: same indices out of the per-device scratch, call after call (the view is overwritten by the next call)
+    for k in (0, 1, 0):
+        idx = ops.frustum_select(cloud, z[f'c2w{k}'], z[f'depth{k}'], int(H), int(W), fx, fy, cx, cy, edge=int(z[f'edge{k}']), reuse=True)
+        assert np.array_equal(idx.cpu().numpy(), z[f'indices{k}']), k
 
 
 def test_frustum_select_full_size_vs_oracle():
