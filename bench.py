@@ -467,6 +467,9 @@ def run_ours(args):
         scene = RenderScene(rank, device, wl, points, n_frames)
     else:
         scene = GpuScene(rank, device, wl, points, n_frames, share_map=args.share_map and world > 1, dist=dist)
+    # the CUDA arm has no CPU-parallel work after the scene is built: keep the intra-op pool small so that N ranks on one host do not
+    # spin 128 OpenMP workers each between the few tiny ATen CPU ops of a step (the cpu_baseline leg calibrates its own count later)
+    torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // max(world, 1))))
     for k in range(args.warmup):
         scene.step(k, False)
     cap0 = scene.captures()
