@@ -11,7 +11,7 @@ export PSL_PARITY_TO_GPURUN_OUT=1
 ( time timeout 1200 python -m pytest tests -m gpu -q --maxfail=8 -p no:cacheprovider -rxX ) > gpurun_out/${T}_tests.log 2>&1
 echo "tests exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/${T}_tests.log | tail -8
 ( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/${T}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/${T}_smoke.log
-( time timeout 500 python bench.py --steps 8 --warmup 3 ) > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; echo "bench c2 exit $?"
+( time timeout 500 python bench.py ) > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; echo "bench c2 exit $?"
 for c in c1 c3 c4 rerender; do
   ( time timeout 500 python bench.py --config $c ) > gpurun_out/${T}_bench_$c.json 2> gpurun_out/${T}_bench_$c.err; echo "bench $c exit $?"
 done
