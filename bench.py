@@ -414,6 +414,47 @@ class RerenderScene:
         return 0
 
 
+class HostSampler:
+    """Diagnostics (PSL_HOST_SAMPLER=1): a thread notes every 4 ms which Python line the main thread is executing (or blocked in, when
+    the callee released the GIL); runs of identical samples longer than 20 ms that are not one of the step's known device syncs
+    are reported in timing.host_stalls."""
+
+    def __init__(self):
+        import threading
+        self.tid = threading.get_ident()
+        self.samples = []
+        self.stop = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        while not self.stop:
+            f = sys._current_frames().get(self.tid)
+            chain = []
+            while f is not None and len(chain) < 5:
+                chain.append(f'{os.path.basename(f.f_code.co_filename)}:{f.f_lineno}:{f.f_code.co_name}')
+                f = f.f_back
+            self.samples.append((time.perf_counter(), ' < '.join(chain)))
+            time.sleep(0.004)
+
+    def report(self):
+        self.stop = True
+        self.th.join()
+        out, i, s = [], 0, self.samples
+        while i < len(s):
+            j = i
+            while j + 1 < len(s) and s[j + 1][1] == s[i][1]:
+                j += 1
+            dt = (s[j][0] - s[i][0]) * 1e3
+            if dt > 20.0:
+                out.append((round(dt, 1), s[i][1]))
+            gap = (s[j + 1][0] - s[j][0]) * 1e3 if j + 1 < len(s) else 0.0
+            if gap > 20.0:
+                out.append((round(gap, 1), 'GIL held after: ' + s[j][1]))
+            i = j + 1
+        return out
+
+
 def timed_steps(scene, steps, first, from_host, dist):
     gc.collect()
     gc.disable()          # a generation-2 collection inside a step stalls the host between two device syncs of the map update (seen
@@ -474,11 +515,13 @@ def run_ours(args):
         scene.step(k, False)
     cap0 = scene.captures()
     ms0 = torch.cuda.memory_stats(device)
+    sampler = HostSampler() if os.environ.get('PSL_HOST_SAMPLER') else None
     clocks = Clocks(local) if rank == 0 else None
     ms, samples, per_step = timed_steps(scene, args.steps, args.warmup, False, dist)
     ms_e2e, samples_e2e, per_step_e2e = timed_steps(scene, args.steps, args.warmup, True, dist)
     clk = clocks.stop() if clocks else None
     recaptures = scene.captures() - cap0
+    host_stalls = sampler.report() if sampler else None
     ms1 = torch.cuda.memory_stats(device)
     alloc_diag = {k: ms1.get(k, 0) - ms0.get(k, 0) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries', 'num_sync_all_streams')}
     alloc_diag['reserved_GB'] = round(ms1.get('reserved_bytes.all.current', 0) / 1e9, 2)
@@ -575,7 +618,7 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
         'timing': {'l2': 'inputs larger than L2 (cloud + features 134 MB at 500k points; saved activations ~290 MB per mapper iteration)',
                    'per_rank_ms_per_step': [round(x, 3) for x in per_rank],
-                   'graph_recaptures_in_timed_region': recaptures, 'allocator_in_timed_region': alloc_diag, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
+                   'graph_recaptures_in_timed_region': recaptures, 'allocator_in_timed_region': alloc_diag, 'host_stalls': host_stalls, 'map_update_ms_per_step': map_ms, 'map_update_ms_each': map_each if map_ms is not None else None,
                    'map_update_host_ms_each': map_host_each if map_ms is not None else None,
                    'map_update_host_parts_ms': scene.map_parts[-2 * args.steps:] if map_ms is not None else None,
                    'points_at_end': scene.npc.pts_num(), 'points_added': getattr(scene, 'added', 0),

@@ -524,6 +524,7 @@ class FusedTracker:
             self._iter()
         self.key = self._graph_key()
         self.captures += 1
+        ops.warm_allocator(self.dev)                       # torch.cuda.graph emptied the allocator's cache on entry: refill it
         for t, k in zip((self.cam, self.best_loss, self.best_cam), keep):
             t.copy_(k)
         self.adam.reset()
@@ -653,6 +654,7 @@ class FusedMapper:
                 self._iter(stage)
             self.graphs[stage] = g
             self.captures += 1
+            ops.warm_allocator(self.dev)
         for _ in range(n_iters - done):
             self.graphs[stage].replay()
         return self.loss

@@ -252,6 +252,7 @@ USE_TENSOR_CORES = os.environ.get('PSL_TC', '1') != '0'      # tcgen05 colour br
 USE_TC_BACKWARD = os.environ.get('PSL_TC_BWD', '1') != '0'    # tcgen05 colour-branch backward (data gradients)
 USE_TC_WGRAD = os.environ.get('PSL_TC_WGRAD', '1') != '0'     # tcgen05 weight-gradient GEMMs of the colour branch
 USE_GEO_MMA = os.environ.get('PSL_GEO_MMA', '1') != '0'           # geometry branch on mma.sync 3xTF32 when its parameters are frozen
+WARM_ALLOCATOR = os.environ.get('PSL_WARM_ALLOC', '1') != '0'     # pre-fill the caching allocator's pools after a graph capture
 INCREMENTAL_HASH = os.environ.get('PSL_HASH_APPEND', '1') != '0'   # add_neural_points: sort + merge the new points only (psl_grid_append)
 USE_H2_BACKWARD = os.environ.get('PSL_H2_BWD', '1') != '0'     # f16-plane colour backward with per-row gradient scaling (psl_color_bwd_h2.cu)
 USE_H2_FORWARD = os.environ.get('PSL_H2', '1') != '0'           # f16-plane, two-tiles-in-flight colour forward (psl_color_h2.cu)
@@ -580,6 +581,19 @@ class RenderSaved:
 
     def tensors(self):
         return tuple(getattr(self, k) for k in self.FIELDS)
+
+
+def warm_allocator(device, large_bytes=1 << 30, small_bytes=128 << 20):
+    """Leave `large_bytes` (one block) and `small_bytes` (2 MB segments) of free memory in the caching allocator's pools.  The
+    per-frame map update allocates tensors whose sizes change from frame to frame (#kept rays, #selected rows); whenever no cached
+    block fits, the allocator calls cudaMalloc, which took 40-100 ms in a process holding the instantiated iteration graphs -- one
+    frame step in twenty.  With the pools pre-filled those requests are served by splitting cached blocks.  Called by the
+    iteration-graph classes after every capture (torch.cuda.graph empties the cache when a capture begins)."""
+    if not WARM_ALLOCATOR:
+        return
+    big = torch.empty(int(large_bytes), dtype=torch.uint8, device=device)
+    small = [torch.empty(1 << 19, dtype=torch.uint8, device=device) for _ in range(max(int(small_bytes) >> 19, 1))]
+    del big, small
 
 
 _TAIL_WS = {}
