@@ -10,8 +10,12 @@
 //   * activations never leave registers: the accumulator fragment of layer i (rows g, g+8; columns 8n+2t, 8n+2t+1) is fed
 //     back as the A fragment of layer i+1 by permuting the reduction index (k-step s, logical k = t / t+4  <->  channel 8s+2t /
 //     8s+2t+1), the permutation being applied once to the weights when they are packed;
-//   * weights: pre-split hi/lo B fragments, one 16-byte load per (k-step, n-tile, lane), read through L1 (122 KB per direction,
-//     shared by every warp of the SM) -- no shared-memory staging, no CTA barrier anywhere in the kernel;
+//   * weights: pre-split hi/lo B fragments, one 16-byte shared-memory load per (k-step, n-tile, lane); the 120 KB image of a
+//     direction is brought in by one bulk copy per block that flies while the warps gather (the first version read it through L1:
+//     38 % of the stall samples sat on those loads, profiles/r02_summary.md); the blocks are persistent over the 16-sample tiles,
+//     so the image is loaded once per SM however large the launch; one __syncthreads at block start, none afterwards;
+//   * rolled layer loop (a fully unrolled tile is 12.5 k instructions executed once: instruction-fetch bound), the two embedding
+//     products (layers 0 and 3) accumulated in ONE pass over the Fourier channels, so sin() is evaluated once and never stored;
 //   * kept for the backward: one 32-bit ReLU mask per sample and layer (20 B / sample instead of 1.4 KB).
 #include "psl_decode.cuh"
 #include "psl_tc.cuh"
