@@ -51,20 +51,6 @@ __device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// one k-step (8 reduction indices) against NT n-tiles: acc[n] += x (16x8, A-fragment order, fp32) * B[n] (8x8)
-template <int NT>
-__device__ __forceinline__ void kstep(float (&acc)[NT][4], float x0, float x1, float x2, float x3, const float4* __restrict__ B, int lane) {
-    uint32_t ah[4], al[4];
-    split(x0, ah[0], al[0]); split(x1, ah[1], al[1]); split(x2, ah[2], al[2]); split(x3, ah[3], al[3]);
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-        const float4 b = __ldg(B + n * 32 + lane);
-        const uint32_t b0h = __float_as_uint(b.x), b1h = __float_as_uint(b.y), b0l = __float_as_uint(b.z), b1l = __float_as_uint(b.w);
-        mma8(acc[n], al, b0h, b1h);
-        mma8(acc[n], ah, b0l, b1l);
-        mma8(acc[n], ah, b0h, b1h);
-    }
-}
 // an accumulator block (columns 8s .. 8s+7 of a 16-row tile) as the A operand of k-step s
 #define PSL_GM_AFRAG(c) (c)[0], (c)[2], (c)[1], (c)[3]
 
@@ -174,7 +160,7 @@ __device__ __forceinline__ void wait_image(unsigned char* smem) { tc::mbar_wait_
 __device__ __forceinline__ float emb_arg(const float* sGB, int j, float x, float y, float z) {
     return fmaf(z, sGB[2 * 96 + j], fmaf(y, sGB[96 + j], x * sGB[j]));
 }
-// k-step against the shared-memory image (same as kstep, LDS instead of LDG)
+// one k-step (8 reduction indices) against NT n-tiles of the shared-memory image: acc[n] += x (16x8, A-fragment order, fp32) * B[n]
 template <int NT>
 __device__ __forceinline__ void kstep_s(float (&acc)[NT][4], float x0, float x1, float x2, float x3, const float4* B, int lane) {
     uint32_t ah[4], al[4];
